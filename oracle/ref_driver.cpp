@@ -1,0 +1,187 @@
+// TEST INFRASTRUCTURE ONLY. Never linked into, imported by, or called from the product path.
+//
+// C-ABI driver around the UNMODIFIED reference translation units
+//   /root/reference/Source/HeatCool/integrate_state_vec_3d.cpp
+//   /root/reference/Source/HeatCool/integrate_state_with_source_3d.cpp
+// (+ the reference's EOS/HeatCool headers and the vendored SUNDIALS 6.3.0 CVODE sources),
+// all compiled where they lie by oracle/Makefile into oracle/_ref/. It plays the part of
+// Exec/HeatCoolTests/nyx_main.cpp:97-104 + Source/Initialization/Nyx_setup.cpp:157-166:
+// build the rate tables, build MultiFabs over caller memory, call the public
+// Nyx::integrate_state_vec / integrate_state_grownvec / integrate_state_struct.
+//
+// CVode() and CVodeFree() are intercepted with -DCVode=nyxref_hook_CVode
+// -DCVodeFree=nyxref_hook_CVodeFree on the two reference TUs only, so that the return flag
+// the reference ignores (integrate_state_vec_3d.cpp:284) and the per-instance counters can be
+// recorded without touching reference sources.
+#include <AMReX_MultiFab.H>
+#include <AMReX_ParmParse.H>
+#include <Nyx.H>
+
+#include <cvode/cvode.h>
+#include <cvode/cvode_diag.h>
+
+using namespace amrex;
+#include <atomic_rates.H>   // reference: tabulate_rates (non-inline, include in exactly one TU)
+
+// ---- definitions the reference expects from Source/Driver/Nyx.cpp:102-201 (same defaults)
+AtomicRates* atomic_rates_glob = nullptr;
+Real Nyx::gamma = 5.0 / 3.0;
+Real Nyx::h_species = 0.76;
+int Nyx::verbose = 0;
+int Nyx::strang_grown_box = 1;
+int Nyx::heat_cool_type = 11;
+int Nyx::sundials_atomic_reductions = -1;
+int Nyx::sundials_alloc_type = 0;
+int Nyx::use_typical_steps = 0;
+int Nyx::use_sundials_constraint = 0;
+int Nyx::use_sundials_fused = 0;
+bool Nyx::sundials_use_tiling = true;
+Real Nyx::sundials_reltol = 1e-4;
+Real Nyx::sundials_abstol = 1e-4;
+// Nyx.cpp:555-568: unset nyx.sundials_tile_size falls back to fabarray.mfiter_tile_size
+IntVect Nyx::sundials_tile_size(1024000, 8, 8);
+int Nyx::inhomo_reion = 0;
+long int Nyx::old_max_sundials_steps = 3;
+long int Nyx::new_max_sundials_steps = 3;
+
+namespace {
+struct InstanceStats { long v[8]; };
+std::vector<InstanceStats> g_stats;
+std::vector<int> g_flags;
+bool g_record = true;
+}
+
+extern "C" {
+
+int nyxref_hook_CVode(void* cvode_mem, realtype tout, N_Vector yout, realtype* tret, int itask) {
+    int flag = CVode(cvode_mem, tout, yout, tret, itask);
+    if (g_record) g_flags.push_back(flag);
+    return flag;
+}
+
+void nyxref_hook_CVodeFree(void** cvode_mem) {
+    if (g_record && cvode_mem && *cvode_mem) {
+        InstanceStats s{};
+        CVodeGetNumSteps(*cvode_mem, &s.v[0]);
+        CVodeGetNumErrTestFails(*cvode_mem, &s.v[1]);
+        CVodeGetNumRhsEvals(*cvode_mem, &s.v[2]);
+        CVodeGetNumNonlinSolvIters(*cvode_mem, &s.v[3]);
+        CVodeGetNumNonlinSolvConvFails(*cvode_mem, &s.v[4]);
+        CVodeGetNumLinSolvSetups(*cvode_mem, &s.v[5]);
+        CVDiagGetNumRhsEvals(*cvode_mem, &s.v[6]);
+        s.v[7] = g_flags.empty() ? 0 : g_flags.back();
+        g_stats.push_back(s);
+    }
+    CVodeFree(cvode_mem);
+}
+
+// Nyx::heatcool_setup (Source/Initialization/Nyx_setup.cpp:157-166)
+int nyxref_init(const char* treecool_path, double mean_rhob) {
+    if (!atomic_rates_glob) atomic_rates_glob = (AtomicRates*)The_Arena()->alloc(sizeof(AtomicRates));
+    tabulate_rates(std::string(treecool_path), mean_rhob);
+    return 0;
+}
+
+// raw view of the reference's AtomicRates (1 + 7*301 + 15*2001 doubles)
+const double* nyxref_rates(long* n_doubles) {
+    if (n_doubles) *n_doubles = long(sizeof(AtomicRates) / sizeof(double));
+    return reinterpret_cast<const double*>(atomic_rates_glob);
+}
+
+// nyx.* ParmParse entries (read by ode_eos_setup, f_rhs_struct.H:45-101) and the Nyx statics
+// parsed in Nyx::read_hydro_params (Source/Driver/Nyx.cpp:474-593)
+int nyxref_set(const char* key, const char* value) {
+    std::string k(key), v(value);
+    std::istringstream is(v);
+    if (k == "nyx.gamma") is >> Nyx::gamma;
+    else if (k == "nyx.h_species") is >> Nyx::h_species;
+    else if (k == "nyx.v") is >> Nyx::verbose;
+    else if (k == "nyx.use_typical_steps") is >> Nyx::use_typical_steps;
+    else if (k == "nyx.use_sundials_constraint") is >> Nyx::use_sundials_constraint;
+    else if (k == "nyx.sundials_use_tiling") is >> Nyx::sundials_use_tiling;
+    else if (k == "nyx.sundials_reltol") is >> Nyx::sundials_reltol;
+    else if (k == "nyx.sundials_abstol") is >> Nyx::sundials_abstol;
+    else if (k == "nyx.sundials_tile_size") { is >> Nyx::sundials_tile_size[0] >> Nyx::sundials_tile_size[1] >> Nyx::sundials_tile_size[2]; }
+    else if (k == "nyx.inhomo_reion") { is >> Nyx::inhomo_reion; ParmParse::table()[k] = v; }
+    else if (k == "nyx.old_max_sundials_steps") is >> Nyx::old_max_sundials_steps;
+    else if (k == "nyx.new_max_sundials_steps") is >> Nyx::new_max_sundials_steps;
+    else if (k == "fabarray.mfiter_tile_size") { is >> FabArrayBase::mfiter_tile_size[0] >> FabArrayBase::mfiter_tile_size[1] >> FabArrayBase::mfiter_tile_size[2]; }
+    else if (k == "omp.num_threads") {
+#ifdef _OPENMP
+        int n; is >> n; omp_set_num_threads(n);
+#endif
+    }
+    else ParmParse::table()[k] = v;
+    return 0;
+}
+
+int nyxref_unset(const char* key) { ParmParse::table().erase(key); return 0; }
+
+int nyxref_max_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+void nyxref_stats_reset(void) { g_stats.clear(); g_flags.clear(); }
+void nyxref_stats_record(int on) { g_record = (on != 0); }
+long nyxref_stats_count(void) { return long(g_stats.size()); }
+// out[8*i + {0..7}] = nst, netf, nfe, nni, ncfn, nsetups, nfeLS, CVode() flag of instance i (MFIter order)
+void nyxref_stats_get(long* out) { for (size_t i = 0; i < g_stats.size(); ++i) std::memcpy(out + 8 * i, g_stats[i].v, sizeof(long) * 8); }
+long nyxref_get_max_steps(int which) { return which ? Nyx::new_max_sundials_steps : Nyx::old_max_sundials_steps; }
+
+static BoxArray make_ba(int nboxes, const int* boxes) {
+    std::vector<Box> b;
+    for (int i = 0; i < nboxes; ++i) b.emplace_back(IntVect(boxes[6 * i], boxes[6 * i + 1], boxes[6 * i + 2]), IntVect(boxes[6 * i + 3], boxes[6 * i + 4], boxes[6 * i + 5]));
+    return BoxArray(b);
+}
+
+// boxes: nboxes x {lo[3], hi[3]} valid boxes; state[i]/diag[i]: FAB i = (box grown by ng) x ncomp, Fortran order.
+// grown=0 -> Nyx::integrate_state_vec (HC/integrate_state_vec_3d.cpp:44); grown=1 -> integrate_state_grownvec (:367)
+int nyxref_integrate_state_vec(int nboxes, const int* boxes, int ng_state, int ng_diag, int ncomp_diag,
+                               double* const* state, double* const* diag, double a, double dt, int grown) {
+    BoxArray ba = make_ba(nboxes, boxes);
+    MultiFab S, D;
+    S.defineAlias(ba, 6, ng_state, state);
+    D.defineAlias(ba, ncomp_diag, ng_diag, diag);
+    Nyx nyx;
+    return grown ? nyx.integrate_state_grownvec(S, D, a, dt) : nyx.integrate_state_vec(S, D, a, dt);
+}
+
+// Nyx::integrate_state_struct (HC/integrate_state_with_source_3d.cpp:50); ng[6]/ptrs in the
+// order S_old, S_new, D_old, hydro_src, IR, reset_src (the reference's argument order)
+int nyxref_integrate_state_struct(int nboxes, const int* boxes, const int* ng, int ncomp_diag,
+                                  double* const* s_old, double* const* s_new, double* const* d_old,
+                                  double* const* hydro_src, double* const* ir, double* const* reset_src,
+                                  double a, double a_end, double dt, int sdc_iter) {
+    BoxArray ba = make_ba(nboxes, boxes);
+    MultiFab S_old, S_new, D_old, H, IR, R;
+    S_old.defineAlias(ba, 6, ng[0], s_old);
+    S_new.defineAlias(ba, 6, ng[1], s_new);
+    D_old.defineAlias(ba, ncomp_diag, ng[2], d_old);
+    H.defineAlias(ba, 6, ng[3], hydro_src);
+    IR.defineAlias(ba, 1, ng[4], ir);
+    R.defineAlias(ba, 1, ng[5], reset_src);
+    Nyx nyx;
+    return nyx.integrate_state_struct(S_old, S_new, D_old, H, IR, R, a, a_end, dt, sdc_iter);
+}
+
+}  // extern "C"
+
+// ---- single-function probes of the reference's device functions (unit parity of the port)
+#include <eos_hc.H>
+extern "C" {
+void nyxref_ion_n(int JH, int JHe, double U, double nh, double ne, double gamma_minus_1, double h_species, double z, double* out4) {
+    Real nhp, nhep, nhepp, t;
+    ion_n_device(atomic_rates_glob, JH, JHe, U, nh, ne, nhp, nhep, nhepp, t, gamma_minus_1, h_species, z);
+    out4[0] = nhp; out4[1] = nhep; out4[2] = nhepp; out4[3] = t;
+}
+void nyxref_eos_T_given_Re(int JH, int JHe, double R, double e, double a, double gamma_minus_1, double h_species, double* T, double* Ne) {
+    nyx_eos_T_given_Re_device(atomic_rates_glob, gamma_minus_1, h_species, JH, JHe, T, Ne, R, e, a);
+}
+void nyxref_interp_to_this_z(double z, double* out6) {
+    interp_to_this_z(atomic_rates_glob, z, out6[0], out6[1], out6[2], out6[3], out6[4], out6[5]);
+}
+}
