@@ -111,3 +111,119 @@ class Reference:
         Ne = C.c_double(0.0)
         self.lib.nyxref_eos_T_given_Re(JH, JHe, R, e, a, gm1, hsp, C.byref(T), C.byref(Ne))
         return T.value, Ne.value
+
+
+# --------------------------------------------------------------------------- the C restatement
+class HcoFab(C.Structure):
+    _fields_ = [("p", _dp), ("jstride", C.c_long), ("kstride", C.c_long), ("nstride", C.c_long),
+                ("lo", C.c_int * 3), ("hi", C.c_int * 3), ("ncomp", C.c_int)]
+
+
+class HcoParams(C.Structure):
+    _fields_ = [("rtol", C.c_double), ("atol_factor", C.c_double), ("h_species", C.c_double), ("gamma_minus_1", C.c_double),
+                ("max_steps", C.c_long), ("use_constraint", C.c_int), ("use_typical_steps", C.c_int), ("old_max_steps", C.c_long),
+                ("uvb_density_A", C.c_double), ("uvb_density_B", C.c_double), ("zhi_flash", C.c_double), ("zheii_flash", C.c_double),
+                ("T_zhi", C.c_double), ("T_zheii", C.c_double), ("inhomo_reion", C.c_int)]
+
+
+STAT_FIELDS = ("nst", "netf", "nfe", "nni", "ncfn", "nsetups", "nfeLS", "flag", "ne_iters", "attempts")
+RATES_DOUBLES = 1 + 7 * 301 + 15 * 2001
+
+
+def fab_of(arr, lo, cls=HcoFab):
+    """arr: C-contiguous (ncomp, nz, ny, nx) float64 covering [lo, lo+shape-1]."""
+    nc, nz, ny, nx = arr.shape
+    f = cls()
+    f.p = arr.ctypes.data_as(_dp)
+    f.jstride, f.kstride, f.nstride = nx, nx * ny, nx * ny * nz
+    f.lo[:] = list(lo)
+    f.hi[:] = [lo[0] + nx - 1, lo[1] + ny - 1, lo[2] + nz - 1]
+    f.ncomp = nc
+    return f
+
+
+class Port:
+    """oracle/hc_oracle.c (scalar per-cell CVODE restatement)."""
+
+    def __init__(self, treecool=TREECOOL, mean_rhob=None):
+        path = os.path.join(HERE, "_build", "libhc_oracle.so")
+        if not os.path.exists(path):
+            build("port")
+        self.lib = lib = C.CDLL(path)
+        if mean_rhob is None:
+            from nyx_b200 import synth
+            mean_rhob = synth.mean_rhob()
+        self.rates_buf = np.zeros(RATES_DOUBLES)
+        self.rp = self.rates_buf.ctypes.data_as(C.c_void_p)
+        lib.hco_tabulate_rates.argtypes = [C.c_char_p, C.c_double, C.c_void_p]
+        rc = lib.hco_tabulate_rates(treecool.encode(), mean_rhob, self.rp)
+        if rc != 0:
+            raise RuntimeError(f"hco_tabulate_rates -> {rc}")
+        lib.hco_default_params.argtypes = [C.POINTER(HcoParams)]
+        lib.hco_ion_n.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_double] * 6 + [_dp]
+        lib.hco_iterate_ne.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_double] * 5 + [_dp]
+        lib.hco_eos_T_given_Re.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, _dp, _dp]
+        lib.hco_interp_to_this_z.argtypes = [C.c_void_p, C.c_double, _dp]
+        lib.hco_f_rhs_rpar.restype = C.c_double
+        lib.hco_f_rhs_rpar.argtypes = [C.c_void_p, C.c_double, _dp, _dp]
+        fp = C.POINTER(HcoFab)
+        ip = C.POINTER(C.c_int)
+        lib.hco_integrate_state_vec.argtypes = [C.c_void_p, C.POINTER(HcoParams), fp, fp, ip, ip, C.c_double, C.c_double, C.c_void_p]
+        lib.hco_integrate_state_struct.argtypes = [C.c_void_p, C.POINTER(HcoParams)] + [fp] * 6 + [ip, ip, C.c_double, C.c_double, C.c_double,
+                                                                                                     C.c_int, C.c_void_p]
+        lib.hco_eos_box.argtypes = [C.c_void_p, C.POINTER(HcoParams), fp, fp, ip, ip, C.c_double]
+
+    def params(self, **kw):
+        p = HcoParams()
+        self.lib.hco_default_params(C.byref(p))
+        for k, v in kw.items():
+            setattr(p, k, v)
+        return p
+
+    def rates(self):
+        return self.rates_buf.copy()
+
+    def ion_n(self, JH, JHe, U, nh, ne, gm1, hsp, z):
+        out = np.zeros(4)
+        self.lib.hco_ion_n(self.rp, JH, JHe, U, nh, ne, gm1, hsp, z, out.ctypes.data_as(_dp))
+        return out
+
+    def eos_T_given_Re(self, JH, JHe, R, e, a, gm1, hsp):
+        T = C.c_double(0.0)
+        Ne = C.c_double(0.0)
+        self.lib.hco_eos_T_given_Re(self.rp, gm1, hsp, JH, JHe, R, e, a, C.byref(T), C.byref(Ne))
+        return T.value, Ne.value
+
+    @staticmethod
+    def _box(lo, hi):
+        return (C.c_int * 3)(*lo), (C.c_int * 3)(*hi)
+
+    def integrate_state_vec(self, state, diag, lo, hi, a, dt, params=None, fab_lo=None, diag_lo=None, want_stats=True):
+        """state/diag: (ncomp, nz, ny, nx) arrays whose first cell is fab_lo/diag_lo (default lo)."""
+        p = params or self.params()
+        sf = fab_of(state, fab_lo or lo)
+        df = fab_of(diag, diag_lo or fab_lo or lo)
+        n = (hi[0] - lo[0] + 1) * (hi[1] - lo[1] + 1) * (hi[2] - lo[2] + 1)
+        st = np.zeros((n, len(STAT_FIELDS)), dtype=np.int64) if want_stats else None
+        l, h = self._box(lo, hi)
+        self.lib.hco_integrate_state_vec(self.rp, C.byref(p), C.byref(sf), C.byref(df), l, h, a, dt,
+                                         st.ctypes.data_as(C.c_void_p) if want_stats else None)
+        return st
+
+    def integrate_state_struct(self, s_old, s_new, diag, hydro_src, reset_src, ir, lo, hi, a, a_end, dt, sdc_iter=0, params=None,
+                               los=None, want_stats=True):
+        p = params or self.params()
+        los = los or [lo] * 6
+        fabs = [fab_of(x, l) for x, l in zip((s_old, s_new, diag, hydro_src, reset_src, ir), los)]
+        n = (hi[0] - lo[0] + 1) * (hi[1] - lo[1] + 1) * (hi[2] - lo[2] + 1)
+        st = np.zeros((n, len(STAT_FIELDS)), dtype=np.int64) if want_stats else None
+        l, h = self._box(lo, hi)
+        self.lib.hco_integrate_state_struct(self.rp, C.byref(p), *[C.byref(f) for f in fabs], l, h, a, a_end, dt, sdc_iter,
+                                            st.ctypes.data_as(C.c_void_p) if want_stats else None)
+        return st
+
+    def eos_box(self, state, diag, lo, hi, a, params=None):
+        p = params or self.params()
+        sf, df = fab_of(state, lo), fab_of(diag, lo)
+        l, h = self._box(lo, hi)
+        self.lib.hco_eos_box(self.rp, C.byref(p), C.byref(sf), C.byref(df), l, h, a)
