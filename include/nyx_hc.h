@@ -1,0 +1,154 @@
+/* nyx_hc.h -- C-ABI of the B200 heating-cooling (HeatCool) reaction integrator.
+ *
+ * This is the drop-in boundary of the hot path of AMReX-Astro/Nyx Lyman-alpha runs
+ * (SURVEY.md section 8b). Plain C types only; FAB memory is described the way
+ * amrex::Array4<Real> describes it, so a host shim can pass `MultiFab::array(mfi)` through
+ * unchanged. Reference interfaces replaced (paths relative to the reference tree):
+ *
+ *   hc_tabulate_rates / hc_tables_upload   <- tabulate_rates()              Source/EOS/atomic_rates.H:10-166
+ *                                             (called from Nyx::heatcool_setup, Source/Initialization/Nyx_setup.cpp:157-166)
+ *   hc_integrate_vec[_batch]               <- Nyx::integrate_state_vec_mfin  Source/HeatCool/integrate_state_vec_3d.cpp:72-365
+ *                                             (callers integrate_state_vec :44-70, integrate_state_grownvec :367-396)
+ *   hc_integrate_struct[_batch]            <- Nyx::integrate_state_struct_mfin Source/HeatCool/integrate_state_with_source_3d.cpp:187-709
+ *   hc_eos_T_given_Re                      <- nyx_eos_T_given_Re_device over a box, the body of Nyx::compute_new_temp
+ *                                             Source/EOS/eos_hc.H:190-220, Source/Driver/Nyx.cpp:2473-2490
+ *   HcParams                               <- the nyx.* run-time flags of the path, Source/Driver/Nyx.cpp:116-181,
+ *                                             Source/HeatCool/f_rhs_struct.H:45-101
+ *   HcStats                                <- CVodeGetNum* counters (integrate_state_with_source_3d.cpp:755-790) and the
+ *                                             CVode() return flag the reference ignores (:585), reduced over cells
+ *
+ * All pointers in HcFab are DEVICE pointers unless the function name ends in _host.
+ * Every function returns 0 on success and a negative HC_ERR_* code otherwise; like the
+ * reference (which ignores the CVode flag) a per-cell integrator failure is NOT an error:
+ * it is counted in HcStats.n_failed. There is no CPU fallback: without a CUDA device every
+ * compute entry point returns HC_ERR_CUDA.
+ */
+#ifndef NYX_HC_H
+#define NYX_HC_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HC_NCOOLFILE 301   /* rows of the TREECOOL UV-background file (atomic_rates_data.H:9)  */
+#define HC_NCOOLTAB 2000   /* temperature table intervals, 2001 entries (atomic_rates_data.H:10) */
+/* number of doubles in the reference's struct AtomicRates: mean_rhob, 7 x 301 UVB columns, 15 x 2001 rate tables */
+#define HC_RATES_DOUBLES (1 + 7 * HC_NCOOLFILE + 15 * (HC_NCOOLTAB + 1))
+
+enum {
+    HC_OK = 0,
+    HC_ERR_CUDA = -1,        /* no device / CUDA runtime error (message via hc_last_error) */
+    HC_ERR_ARG = -2,         /* bad argument */
+    HC_ERR_NO_TABLES = -3,   /* hc_tables_upload has not been called on this device */
+    HC_ERR_IO = -4,          /* TREECOOL file missing or malformed */
+    HC_ERR_TREECOOL_LEN = -5 /* more than HC_NCOOLFILE rows (the reference aborts, atomic_rates.H:37-51) */
+};
+
+/* amrex::Array4<Real> (AMReX_Array4.H:59-93): element (i,j,k,n) lives at
+ * p[(i-lo[0]) + (j-lo[1])*jstride + (k-lo[2])*kstride + n*nstride]; hi is inclusive. */
+typedef struct HcFab {
+    double* p;
+    long long jstride, kstride, nstride;
+    int lo[3], hi[3];
+    int ncomp;
+    int pad_;
+} HcFab;
+
+/* amrex::Box, inclusive bounds: the tile the reference passes as `tbx` */
+typedef struct HcBox {
+    int lo[3], hi[3];
+} HcBox;
+
+typedef struct HcParams {
+    double rtol;              /* nyx.sundials_reltol (1e-4) */
+    double atol_factor;       /* nyx.sundials_abstol (1e-4): abstol_i = atol_factor * e_i(t0) */
+    double h_species;         /* nyx.h_species (0.76) */
+    double gamma_minus_1;     /* nyx.gamma - 1; used by the SDC path only (Strang hard-wires 2/3, f_rhs.H:133) */
+    double uvb_density_A;     /* nyx.uvb_density_A (1.0), SDC path */
+    double uvb_density_B;     /* nyx.uvb_density_B (0.0), SDC path */
+    double zhi_flash;         /* nyx.reionization_zHI_flash  (-1 = off) */
+    double zheii_flash;       /* nyx.reionization_zHeII_flash (-1 = off) */
+    double T_zhi;             /* nyx.reionization_T_zHI */
+    double T_zheii;           /* nyx.reionization_T_zHeII */
+    long long max_steps;      /* CVodeSetMaxNumSteps (2000) */
+    long long old_max_steps;  /* with use_typical_steps: CVodeSetMaxStep(dt / old_max_steps) */
+    int use_typical_steps;    /* nyx.use_typical_steps (0) */
+    int use_constraint;       /* nyx.use_sundials_constraint (0): CVodeSetConstraints(y > 0) */
+    int inhomo_reion;         /* nyx.inhomo_reion (0): per-cell z_HI from diag component 2 */
+    int pad_;
+} HcParams;
+
+typedef struct HcStats {
+    long long n_cells;        /* cells integrated */
+    long long n_failed;       /* cells whose CVODE-equivalent integration returned a flag < 0 */
+    long long n_floor;        /* cells that hit the negative-energy floor (T = 10 K, ne = 0) */
+    long long sum_nst;        /* internal BDF steps, summed / max over cells */
+    long long max_nst;
+    long long sum_nfe;        /* RHS evaluations (CVodeGetNumRhsEvals) */
+    long long sum_nfe_ls;     /* RHS evaluations by the diagonal Jacobian setup (CVDiagGetNumRhsEvals) */
+    long long sum_netf;       /* error-test failures */
+    long long sum_nni;        /* Newton iterations */
+    long long sum_ncfn;       /* nonlinear convergence failures (CVodeGetNumNonlinSolvConvFails) */
+    long long sum_nsetups;    /* Jacobian setups */
+    long long sum_ne_iters;   /* iterate_ne Newton iterations over all RHS evaluations and finalize solves */
+    long long sum_attempts;   /* step attempts (predict + nonlinear solve) */
+    long long sum_eos;        /* finalize EOS solves */
+} HcStats;
+
+/* optional per-cell record for parity checks, x-fastest over the tile (tiles concatenated for _batch) */
+typedef struct HcCellStat {
+    int nst, netf, nfe, nni, ncfn, nsetups, nfe_ls, flag;
+} HcCellStat;
+
+const char* hc_last_error(void);
+const char* hc_version(void);
+
+void hc_default_params(HcParams* p);
+
+/* A1: build the reference's AtomicRates image (HC_RATES_DOUBLES doubles, same member order) on the host.
+ * Pure host code, no device needed. */
+int hc_tabulate_rates(const char* treecool_file, double mean_rhob, double* rates_out);
+/* Upload a rates image to the current device (interleaved for the kernels); once per device. */
+int hc_tables_upload(const double* rates, size_t n_doubles);
+/* interp_to_this_z (eos_hc.H:10-49) on the host copy kept by hc_tables_upload: out6 = ggh0,gghe0,gghep,eh0,ehe0,ehep */
+int hc_uvb_at_z(double z, double* out6);
+
+/* Strang path: integrate de/dt over [0, dt] for every cell of `tile`, update state(Eint,Eden) and diag(Temp,Ne)
+ * in place. stats may be NULL; cell_stats (device pointer) may be NULL. stream is a cudaStream_t (NULL = default). */
+int hc_integrate_vec(const HcFab* state, const HcFab* diag, HcBox tile, double a, double dt, const HcParams* prm,
+                     HcStats* stats, HcCellStat* cell_stats, void* stream);
+int hc_integrate_vec_batch(int ntiles, const HcFab* state, const HcFab* diag, const HcBox* tiles, double a, double dt,
+                           const HcParams* prm, HcStats* stats, HcCellStat* cell_stats, void* stream);
+
+/* SDC path (argument order of integrate_state_struct_mfin: state, diag, state_n, hydro_src, reset_src, IR) */
+int hc_integrate_struct(const HcFab* s_old, const HcFab* diag, const HcFab* s_new, const HcFab* hydro_src,
+                        const HcFab* reset_src, const HcFab* ir, HcBox tile, double a, double a_end, double dt, int sdc_iter,
+                        const HcParams* prm, HcStats* stats, HcCellStat* cell_stats, void* stream);
+int hc_integrate_struct_batch(int ntiles, const HcFab* s_old, const HcFab* diag, const HcFab* s_new, const HcFab* hydro_src,
+                              const HcFab* reset_src, const HcFab* ir, const HcBox* tiles, double a, double a_end, double dt,
+                              int sdc_iter, const HcParams* prm, HcStats* stats, HcCellStat* cell_stats, void* stream);
+
+/* compute_new_temp core: diag(Temp,Ne) = EOS(state(Density), state(Eint)/state(Density), a) with JH = JHe = 1 */
+int hc_eos_T_given_Re(const HcFab* state, const HcFab* diag, HcBox tile, double a, const HcParams* prm, HcStats* stats,
+                      void* stream);
+
+/* Host-buffer variants for CPU builds of the host application (and the end-to-end bench): same semantics,
+ * HcFab.p are HOST pointers; the call stages H2D, runs, and stages the mutated components D2H. */
+int hc_integrate_vec_host(int ntiles, const HcFab* state, const HcFab* diag, const HcBox* tiles, double a, double dt,
+                          const HcParams* prm, HcStats* stats);
+int hc_integrate_struct_host(int ntiles, const HcFab* s_old, const HcFab* diag, const HcFab* s_new, const HcFab* hydro_src,
+                             const HcFab* reset_src, const HcFab* ir, const HcBox* tiles, double a, double a_end, double dt,
+                             int sdc_iter, const HcParams* prm, HcStats* stats);
+
+/* measured FP64 FMA throughput of the current device in FLOP/s (2 flops per DFMA), for roofline denominators */
+int hc_measure_fp64_peak(double* flops_per_s);
+
+/* blocks until work queued on `stream` is done (cudaStreamSynchronize) */
+int hc_sync(void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,197 @@
+"""ctypes binding of the C-ABI in include/nyx_hc.h (libnyx_hc.so, built in-tree by __graft_entry__.build()).
+
+This is the host-side handle tests and bench.py use; a C++ host application links the same
+library directly. There is no fallback: if the library is missing or no
+CUDA device is present, every compute call raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "csrc", "libnyx_hc.so")
+RATES_DOUBLES = 1 + 7 * 301 + 15 * 2001
+
+_dp = C.POINTER(C.c_double)
+
+
+class HcFab(C.Structure):
+    _fields_ = [("p", C.c_void_p), ("jstride", C.c_longlong), ("kstride", C.c_longlong), ("nstride", C.c_longlong),
+                ("lo", C.c_int * 3), ("hi", C.c_int * 3), ("ncomp", C.c_int), ("pad_", C.c_int)]
+
+
+class HcBox(C.Structure):
+    _fields_ = [("lo", C.c_int * 3), ("hi", C.c_int * 3)]
+
+
+class HcParams(C.Structure):
+    _fields_ = [("rtol", C.c_double), ("atol_factor", C.c_double), ("h_species", C.c_double), ("gamma_minus_1", C.c_double),
+                ("uvb_density_A", C.c_double), ("uvb_density_B", C.c_double), ("zhi_flash", C.c_double), ("zheii_flash", C.c_double),
+                ("T_zhi", C.c_double), ("T_zheii", C.c_double), ("max_steps", C.c_longlong), ("old_max_steps", C.c_longlong),
+                ("use_typical_steps", C.c_int), ("use_constraint", C.c_int), ("inhomo_reion", C.c_int), ("pad_", C.c_int)]
+
+
+STATS_FIELDS = ("n_cells", "n_failed", "n_floor", "sum_nst", "max_nst", "sum_nfe", "sum_nfe_ls", "sum_netf", "sum_nni",
+                "sum_ncfn", "sum_nsetups", "sum_ne_iters", "sum_attempts", "sum_eos")
+
+
+class HcStats(C.Structure):
+    _fields_ = [(n, C.c_longlong) for n in STATS_FIELDS]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n in STATS_FIELDS}
+
+
+CELLSTAT_FIELDS = ("nst", "netf", "nfe", "nni", "ncfn", "nsetups", "nfe_ls", "flag")
+CELLSTAT_DTYPE = np.dtype([(n, np.int32) for n in CELLSTAT_FIELDS])
+
+
+def make_fab(ptr, lo, shape_xyz, ncomp):
+    """HcFab over a buffer holding (ncomp, nz, ny, nx) doubles, x fastest, first cell = lo."""
+    nx, ny, nz = shape_xyz
+    f = HcFab()
+    f.p = ptr
+    f.jstride, f.kstride, f.nstride = nx, nx * ny, nx * ny * nz
+    f.lo[:] = list(lo)
+    f.hi[:] = [lo[0] + nx - 1, lo[1] + ny - 1, lo[2] + nz - 1]
+    f.ncomp = ncomp
+    return f
+
+
+def fab_of_numpy(arr, lo):
+    nc, nz, ny, nx = arr.shape
+    assert arr.dtype == np.float64 and arr.flags["C_CONTIGUOUS"]
+    return make_fab(arr.ctypes.data, lo, (nx, ny, nz), nc)
+
+
+def fab_of_torch(t, lo):
+    nc, nz, ny, nx = t.shape
+    assert t.is_contiguous() and t.element_size() == 8
+    return make_fab(t.data_ptr(), lo, (nx, ny, nz), nc)
+
+
+def make_box(lo, hi):
+    b = HcBox()
+    b.lo[:] = list(lo)
+    b.hi[:] = list(hi)
+    return b
+
+
+def default_params_struct(setter):
+    p = HcParams()
+    setter(C.byref(p))
+    return p
+
+
+def declare(lib, prefix="hc_"):
+    fp, bp, pp, sp = C.POINTER(HcFab), C.POINTER(HcBox), C.POINTER(HcParams), C.POINTER(HcStats)
+    lib.hc_last_error.restype = C.c_char_p
+    lib.hc_version.restype = C.c_char_p
+    lib.hc_default_params.argtypes = [pp]
+    lib.hc_tabulate_rates.argtypes = [C.c_char_p, C.c_double, _dp]
+    lib.hc_tables_upload.argtypes = [_dp, C.c_size_t]
+    lib.hc_uvb_at_z.argtypes = [C.c_double, _dp]
+    lib.hc_integrate_vec.argtypes = [fp, fp, HcBox, C.c_double, C.c_double, pp, sp, C.c_void_p, C.c_void_p]
+    lib.hc_integrate_vec_batch.argtypes = [C.c_int, fp, fp, bp, C.c_double, C.c_double, pp, sp, C.c_void_p, C.c_void_p]
+    lib.hc_integrate_struct.argtypes = [fp] * 6 + [HcBox, C.c_double, C.c_double, C.c_double, C.c_int, pp, sp, C.c_void_p, C.c_void_p]
+    lib.hc_integrate_struct_batch.argtypes = [C.c_int] + [fp] * 6 + [bp, C.c_double, C.c_double, C.c_double, C.c_int, pp, sp,
+                                                                      C.c_void_p, C.c_void_p]
+    lib.hc_eos_T_given_Re.argtypes = [fp, fp, HcBox, C.c_double, pp, sp, C.c_void_p]
+    lib.hc_integrate_vec_host.argtypes = [C.c_int, fp, fp, bp, C.c_double, C.c_double, pp, sp]
+    lib.hc_integrate_struct_host.argtypes = [C.c_int] + [fp] * 6 + [bp, C.c_double, C.c_double, C.c_double, C.c_int, pp, sp]
+    lib.hc_measure_fp64_peak.argtypes = [_dp]
+    lib.hc_sync.argtypes = [C.c_void_p]
+    return lib
+
+
+class HcError(RuntimeError):
+    pass
+
+
+class NyxHC:
+    """Thin handle on libnyx_hc.so."""
+
+    def __init__(self, path=LIB_PATH):
+        if not os.path.exists(path):
+            raise HcError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` (no CPU fallback exists)")
+        self.lib = declare(C.CDLL(path))
+
+    def check(self, rc):
+        if rc != 0:
+            raise HcError(f"nyx_hc error {rc}: {self.lib.hc_last_error().decode()}")
+
+    def default_params(self, **kw):
+        p = HcParams()
+        self.lib.hc_default_params(C.byref(p))
+        for k, v in kw.items():
+            setattr(p, k, v)
+        return p
+
+    def tabulate_rates(self, treecool, mean_rhob):
+        out = np.zeros(RATES_DOUBLES)
+        self.check(self.lib.hc_tabulate_rates(treecool.encode(), mean_rhob, out.ctypes.data_as(_dp)))
+        return out
+
+    def tables_upload(self, rates):
+        rates = np.ascontiguousarray(rates, dtype=np.float64)
+        self.check(self.lib.hc_tables_upload(rates.ctypes.data_as(_dp), rates.size))
+
+    def uvb_at_z(self, z):
+        out = np.zeros(6)
+        self.check(self.lib.hc_uvb_at_z(z, out.ctypes.data_as(_dp)))
+        return out
+
+    @staticmethod
+    def _arr(items, cls):
+        a = (cls * len(items))()
+        for i, x in enumerate(items):
+            a[i] = x
+        return a
+
+    def integrate_vec_batch(self, state_fabs, diag_fabs, tiles, a, dt, params=None, cell_stats_ptr=None, stream=None, want_stats=True):
+        p = params or self.default_params()
+        st = HcStats()
+        n = len(tiles)
+        self.check(self.lib.hc_integrate_vec_batch(n, self._arr(state_fabs, HcFab), self._arr(diag_fabs, HcFab), self._arr(tiles, HcBox),
+                                                   a, dt, C.byref(p), C.byref(st) if want_stats else None, cell_stats_ptr, stream))
+        return st
+
+    def integrate_struct_batch(self, s_old, diag, s_new, hydro_src, reset_src, ir, tiles, a, a_end, dt, sdc_iter=0, params=None,
+                               cell_stats_ptr=None, stream=None, want_stats=True):
+        p = params or self.default_params()
+        st = HcStats()
+        n = len(tiles)
+        arrs = [self._arr(x, HcFab) for x in (s_old, diag, s_new, hydro_src, reset_src, ir)]
+        self.check(self.lib.hc_integrate_struct_batch(n, *arrs, self._arr(tiles, HcBox), a, a_end, dt, sdc_iter, C.byref(p),
+                                                      C.byref(st) if want_stats else None, cell_stats_ptr, stream))
+        return st
+
+    def integrate_vec_host(self, state_fabs, diag_fabs, tiles, a, dt, params=None):
+        p = params or self.default_params()
+        st = HcStats()
+        self.check(self.lib.hc_integrate_vec_host(len(tiles), self._arr(state_fabs, HcFab), self._arr(diag_fabs, HcFab),
+                                                  self._arr(tiles, HcBox), a, dt, C.byref(p), C.byref(st)))
+        return st
+
+    def integrate_struct_host(self, s_old, diag, s_new, hydro_src, reset_src, ir, tiles, a, a_end, dt, sdc_iter=0, params=None):
+        p = params or self.default_params()
+        st = HcStats()
+        arrs = [self._arr(x, HcFab) for x in (s_old, diag, s_new, hydro_src, reset_src, ir)]
+        self.check(self.lib.hc_integrate_struct_host(len(tiles), *arrs, self._arr(tiles, HcBox), a, a_end, dt, sdc_iter, C.byref(p),
+                                                     C.byref(st)))
+        return st
+
+    def eos_T_given_Re(self, state_fab, diag_fab, tile, a, params=None, stream=None):
+        p = params or self.default_params()
+        st = HcStats()
+        self.check(self.lib.hc_eos_T_given_Re(C.byref(state_fab), C.byref(diag_fab), tile, a, C.byref(p), C.byref(st), stream))
+        return st
+
+    def measure_fp64_peak(self):
+        v = C.c_double()
+        self.check(self.lib.hc_measure_fp64_peak(C.byref(v)))
+        return v.value
+
+    def sync(self, stream=None):
+        self.check(self.lib.hc_sync(stream))

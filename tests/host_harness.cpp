@@ -1,0 +1,93 @@
+// TEST INFRASTRUCTURE ONLY: runs the product's per-cell state machine (nyx_b200/csrc/hc_device.cuh), compiled for
+// the HOST, one lane at a time, so that its control flow and arithmetic can be compared bit-for-bit with the
+// oracle in a container without a GPU. The product itself never runs this path (no CPU fallback): the C-ABI
+// library only launches the CUDA kernels.
+#include <vector>
+
+#include "../nyx_b200/csrc/hc_host.hpp"
+
+using namespace hc;
+
+namespace {
+struct View {
+    double* p; long long js, ks, ns; int lo[3];
+    double& operator()(int i, int j, int k, int n) const { return p[(i - lo[0]) + (j - lo[1]) * js + (k - lo[2]) * ks + n * ns]; }
+};
+View view(const HcFab* f) { return View{f->p, f->jstride, f->kstride, f->nstride, {f->lo[0], f->lo[1], f->lo[2]}}; }
+void put_stats(HcCellStat* cs, long idx, int nst, int netf, int nfe, int nni, int nnf, int nsetups, int nfe_ls, int flag) {
+    if (!cs) return;
+    cs[idx] = HcCellStat{nst, netf, nfe, nni, nnf, nsetups, nfe_ls, flag};
+}
+}  // namespace
+
+extern "C" {
+
+int hh_tabulate_rates(const char* file, double mean_rhob, double* out) { return tabulate_rates(file, mean_rhob, out); }
+
+int hh_integrate_vec(const double* rates, const HcParams* prm, const HcFab* state, const HcFab* diag, HcBox tile, double a, double dt,
+                     HcCellStat* cs) {
+    std::vector<double> ion, cool;
+    interleave_tables(rates, ion, cool);
+    Tables tb{ion.data(), cool.data()};
+    const Consts k = make_consts_vec(rates, *prm, a, dt);
+    View S = view(state), D = view(diag);
+    long idx = 0;
+    for (int kk = tile.lo[2]; kk <= tile.hi[2]; ++kk) for (int j = tile.lo[1]; j <= tile.hi[1]; ++j) for (int i = tile.lo[0]; i <= tile.hi[0]; ++i, ++idx) {
+        Lane<PATH_VEC> ln;
+        ln.rho = S(i, j, kk, 0);
+        ln.e0 = S(i, j, kk, 5) / ln.rho;
+        ln.abstol = nv_scale(k.atol_factor, ln.e0);
+        ln.jh = 1.0;
+        ln.lastT = D(i, j, kk, 0); ln.lastNe = D(i, j, kk, 1);
+        ln.start(k);
+        while (ln.active()) { const double f = ln.eval_request(tb, k); ln.resume(k, f); }
+        D(i, j, kk, 0) = ln.outT; D(i, j, kk, 1) = ln.outNe;
+        S(i, j, kk, 5) += S(i, j, kk, 0) * (ln.e_final - ln.e0);
+        S(i, j, kk, 4) += S(i, j, kk, 0) * (ln.e_final - ln.e0);
+        put_stats(cs, idx, ln.nst, ln.netf, ln.nfe, ln.nni, ln.nnf, ln.nsetups, ln.nfe_ls, ln.flag);
+    }
+    return 0;
+}
+
+int hh_integrate_struct(const double* rates, const HcParams* prm, const HcFab* s_old, const HcFab* diag, const HcFab* s_new,
+                        const HcFab* hydro_src, const HcFab* reset_src, const HcFab* ir, HcBox tile, double a, double a_end, double dt,
+                        int sdc_iter, HcCellStat* cs) {
+    std::vector<double> ion, cool;
+    interleave_tables(rates, ion, cool);
+    Tables tb{ion.data(), cool.data()};
+    const Consts k = make_consts_struct(rates, *prm, a, a_end, dt, sdc_iter);
+    View S = view(s_old), D = view(diag), N = view(s_new), H = view(hydro_src), R = view(reset_src), I = view(ir);
+    long idx = 0;
+    for (int kk = tile.lo[2]; kk <= tile.hi[2]; ++kk) for (int j = tile.lo[1]; j <= tile.hi[1]; ++j) for (int i = tile.lo[0]; i <= tile.hi[0]; ++i, ++idx) {
+        Lane<PATH_STRUCT> ln;
+        ln.rho = S(i, j, kk, 0);
+        const double rhoe0 = S(i, j, kk, 5);
+        ln.e0 = rhoe0 / ln.rho;
+        ln.abstol = nv_scale(k.atol_factor, ln.e0);
+        ln.jh = (double)k.JH0;
+        ln.lastT = D(i, j, kk, 0); ln.lastNe = D(i, j, kk, 1);
+        ln.rho_src = ln.rhoe_src = ln.e_src = ln.reset_src = 0.0; ln.zhi = 0.0;
+        if (k.sdc_has_src) {   // ode_eos_initialize_arrays f_rhs_struct.H:186-193
+            ln.rho_src = H(i, j, kk, 0) / dt;
+            ln.rhoe_src = H(i, j, kk, 5) / dt;
+            ln.reset_src = R(i, j, kk, 0);
+            ln.e_src = (((k.asq * rhoe0 + dt * ln.rhoe_src) / k.aendsq + ln.reset_src) / (ln.rho + dt * ln.rho_src) - ln.e0) / dt;
+        }
+        if (k.inhomo) { ln.zhi = D(i, j, kk, 2); ln.jh = (k.z > ln.zhi) ? 0.0 : 1.0; }
+        ln.rho_out = N(i, j, kk, 0); ln.rhoe_new = N(i, j, kk, 5);
+        ln.start(k);
+        while (ln.active()) { const double f = ln.eval_request(tb, k); ln.resume(k, f); }
+        D(i, j, kk, 0) = ln.outT; D(i, j, kk, 1) = ln.outNe;
+        if (k.sdc_has_src) {
+            I(i, j, kk, 0) = ln.IR;
+            N(i, j, kk, 5) = N(i, j, kk, 5) + dt * k.ahalf * ln.IR / k.aendsq;
+            N(i, j, kk, 4) = N(i, j, kk, 4) + dt * k.ahalf * ln.IR / k.aendsq;
+        } else {
+            S(i, j, kk, 5) += S(i, j, kk, 0) * (ln.e_final - ln.e0);
+            S(i, j, kk, 4) += S(i, j, kk, 0) * (ln.e_final - ln.e0);
+        }
+        put_stats(cs, idx, ln.nst, ln.netf, ln.nfe, ln.nni, ln.nnf, ln.nsetups, ln.nfe_ls, ln.flag);
+    }
+    return 0;
+}
+}
