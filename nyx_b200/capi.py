@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "csrc", "libnyx_hc.so")
+LIB_PATH = os.environ.get("NYX_HC_LIB") or os.path.join(HERE, "csrc", "libnyx_hc.so")   # NYX_HC_LIB: build-variant experiments only
 RATES_DOUBLES = 1 + 7 * 301 + 15 * 2001
 
 _dp = C.POINTER(C.c_double)

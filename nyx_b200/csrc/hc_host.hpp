@@ -101,13 +101,18 @@ inline Uvb uvb_at_z(const double* R, double z) {
     return u;
 }
 
-// interleave the 15 tables into two row-major [NTAB+1][8] arrays (one padding row so row j+1 always exists)
-inline void interleave_tables(const double* R, std::vector<double>& ion, std::vector<double>& cool) {
-    ion.assign((size_t)(NTAB + 1) * TABLE_ROW, 0.0);
-    cool.assign((size_t)(NTAB + 1) * TABLE_ROW, 0.0);
+// re-layout of the 15 tables for the kernels (one padding row so row j+1 always exists):
+//   ionx [NTAB+1][6]  AlphaHp, AlphaHep, AlphaHepp, Alphad, GammaeH0, GammaeHe0
+//   iony [NTAB+1]     GammaeHep
+//   cool [NTAB+1][8]  BetaH0, BetaHe0, BetaHep, Betaff1, Betaff4, RecHp, RecHep, RecHepp
+inline void interleave_tables(const double* R, std::vector<double>& ionx, std::vector<double>& iony, std::vector<double>& cool) {
+    ionx.assign((size_t)(NTAB + 1) * IONX_ROW, 0.0);
+    iony.assign((size_t)(NTAB + 1) + 1, 0.0);
+    cool.assign((size_t)(NTAB + 1) * COOL_ROW, 0.0);
     for (int j = 0; j < NTAB; ++j) {
-        for (int c = 0; c < 7; ++c) ion[(size_t)j * TABLE_ROW + c] = R[OFF_TAB0 + c * NTAB + j];
-        for (int c = 0; c < 8; ++c) cool[(size_t)j * TABLE_ROW + c] = R[OFF_TAB0 + (7 + c) * NTAB + j];
+        for (int c = 0; c < IONX_ROW; ++c) ionx[(size_t)j * IONX_ROW + c] = R[OFF_TAB0 + c * NTAB + j];
+        iony[j] = R[OFF_TAB0 + 6 * NTAB + j];
+        for (int c = 0; c < COOL_ROW; ++c) cool[(size_t)j * COOL_ROW + c] = R[OFF_TAB0 + (7 + c) * NTAB + j];
     }
 }
 

@@ -27,9 +27,27 @@ namespace {
 
 using namespace hc;
 
-constexpr int THREADS = 512;               // 16 warps per SM
-constexpr int ION_ROWS = NTAB + 1;         // one padding row: row j+1 always exists
-constexpr size_t ION_SMEM_BYTES = (size_t)ION_ROWS * TABLE_ROW * sizeof(double);   // 128,128 B
+#ifndef HC_THREADS
+#define HC_THREADS 512                     // lanes (cells in flight) per SM; one persistent CTA per SM
+#endif
+constexpr int THREADS = HC_THREADS;
+constexpr int TAB_ROWS = NTAB + 1;         // one padding row: row j+1 always exists
+constexpr int CHUNK_MAX = 256;             // cells per work-queue chunk (a piece of one x-row of a tile)
+// dynamic shared memory: [ionx 2002 x 48 B][iony 2003 x 8 B, padded to 16][lane arrays ARR_DOUBLES x THREADS x 8 B]
+constexpr size_t SM_IONX = (size_t)TAB_ROWS * IONX_ROW * sizeof(double);
+constexpr size_t SM_IONY = (((size_t)TAB_ROWS + 1) * sizeof(double) + 15) / 16 * 16;
+constexpr size_t SM_ARR = (size_t)ARR_DOUBLES * THREADS * sizeof(double);
+constexpr size_t SMEM_INTEGRATE = SM_IONX + SM_IONY + SM_ARR;
+constexpr size_t SMEM_EOS = SM_IONX + SM_IONY;
+static_assert(SMEM_INTEGRATE <= 227 * 1024, "shared memory budget of one sm_100 CTA");
+
+// dynamic shared memory of both kernels, and the lanes' array storage inside it (slot-major, lane-minor: conflict-free)
+extern __shared__ __align__(16) unsigned char s_raw[];
+struct ArrSmem {
+    double* p;   // this lane's slot 0
+    __device__ __forceinline__ double& at(int slot) const { return p[slot * THREADS]; }
+};
+template <int PATH> using KLane = Lane<PATH, ArrSmem>;
 
 enum Comp { DENS = 0, EDEN = 4, EINT = 5, TEMP = 0, NE = 1, ZHI = 2 };
 enum FabSlot { F_STATE = 0, F_DIAG = 1, F_SNEW = 2, F_HSRC = 3, F_RSRC = 4, F_IR = 5 };
@@ -38,7 +56,10 @@ struct TileDesc {
     HcFab f[6];
     int lo[3];
     int nx, ny, nz;
-    long long offset;   // global index of this tile's first cell
+    int cpr;                  // chunks per x-row
+    int chunk_len;            // cells per chunk (last chunk of a row may be shorter)
+    long long chunk_begin;    // global index of this tile's first chunk
+    long long offset;         // global index of this tile's first cell (cell_stats ordering)
 };
 
 struct KernelArgs {
@@ -46,192 +67,248 @@ struct KernelArgs {
     const TileDesc* tiles;
     int ntiles;
     long long ncells;
+    long long nchunks;
     unsigned long long* queue;
     unsigned long long* dstats;   // HcStats as 14 x u64
     HcCellStat* cell_stats;
-    const double* ion;
+    const double* ionx;
+    const double* iony;
     const double* cool;
 };
 
 enum StatSlot { S_CELLS = 0, S_FAILED, S_FLOOR, S_NST, S_MAXNST, S_NFE, S_NFELS, S_NETF, S_NNI, S_NCFN, S_NSETUPS, S_NEITERS, S_ATTEMPTS, S_EOS, S_COUNT };
 static_assert(S_COUNT * sizeof(long long) == sizeof(HcStats), "HcStats layout");
 
-__device__ __forceinline__ double& fab_at(const HcFab& f, int i, int j, int k, int n) {
-    return f.p[(i - f.lo[0]) + (long long)(j - f.lo[1]) * f.jstride + (long long)(k - f.lo[2]) * f.kstride + (long long)n * f.nstride];
+__device__ __forceinline__ long long fab_off(const HcFab& f, int i, int j, int k) {
+    return (long long)(i - f.lo[0]) + (long long)(j - f.lo[1]) * f.jstride + (long long)(k - f.lo[2]) * f.kstride;
 }
 
-__device__ __forceinline__ const TileDesc& find_tile(const TileDesc* tiles, int ntiles, long long id) {
+__device__ __forceinline__ int find_tile_by_chunk(const TileDesc* tiles, int ntiles, long long chunk) {
     int lo = 0, hi = ntiles - 1;
     while (lo < hi) {
         const int mid = (lo + hi + 1) >> 1;
-        if (tiles[mid].offset <= id) lo = mid; else hi = mid - 1;
+        if (tiles[mid].chunk_begin <= chunk) lo = mid; else hi = mid - 1;
     }
-    return tiles[lo];
+    return lo;
 }
 
-__device__ __forceinline__ void cell_ijk(const TileDesc& t, long long id, int& i, int& j, int& k) {
-    const long long loc = id - t.offset;
-    const int plane = t.nx * t.ny;
-    const int kk = (int)(loc / plane);
-    const int rem = (int)(loc - (long long)kk * plane);
-    const int jj = rem / t.nx;
-    i = t.lo[0] + (rem - jj * t.nx); j = t.lo[1] + jj; k = t.lo[2] + kk;
+// stage the ionization tables into shared memory (16-byte vector copies)
+__device__ __forceinline__ void stage_tables(const KernelArgs& a, double* s_ionx, double* s_iony) {
+    const double2* src = reinterpret_cast<const double2*>(a.ionx);
+    double2* dst = reinterpret_cast<double2*>(s_ionx);
+#pragma unroll 2
+    for (int i = threadIdx.x; i < TAB_ROWS * IONX_ROW / 2; i += blockDim.x) dst[i] = __ldg(src + i);
+#pragma unroll 1
+    for (int i = threadIdx.x; i < TAB_ROWS + 1; i += blockDim.x) s_iony[i] = __ldg(a.iony + i);
 }
+
+// per-thread running totals of the diagnostics (two 32-bit counters per word), reduced once at the end of the kernel
+struct Totals {
+    unsigned long long w[7];
+    unsigned int max_nst;
+};
 
 // gather one cell into a lane (HOT LOOP A of the reference: integrate_state_vec_3d.cpp:227-233,
 // ode_eos_initialize_arrays f_rhs_struct.H:180-209) and start its integration
 template <int PATH>
-__device__ __forceinline__ void load_cell(Lane<PATH>& ln, const KernelArgs& a, long long id) {
-    const TileDesc& t = find_tile(a.tiles, a.ntiles, id);
-    int i, j, k; cell_ijk(t, id, i, j, k);
+__device__ __forceinline__ void load_cell(KLane<PATH>& ln, const KernelArgs& a, const TileDesc& t, int i, int j, int k) {
     const Consts& c = a.k;
-    ln.rho = fab_at(t.f[F_STATE], i, j, k, DENS);
-    const double rhoe0 = fab_at(t.f[F_STATE], i, j, k, EINT);
+    const long long so = fab_off(t.f[F_STATE], i, j, k);
+    ln.rho = t.f[F_STATE].p[so + DENS * t.f[F_STATE].nstride];
+    const double rhoe0 = t.f[F_STATE].p[so + EINT * t.f[F_STATE].nstride];
     ln.e0 = rhoe0 / ln.rho;
     ln.abstol = nv_scale(c.atol_factor, ln.e0);
-    ln.lastT = fab_at(t.f[F_DIAG], i, j, k, TEMP);
-    ln.lastNe = fab_at(t.f[F_DIAG], i, j, k, NE);
     ln.lastNh = 1.0;
     ln.jh = (double)c.JH0;
     if (PATH == PATH_STRUCT) {
+        const long long dof = fab_off(t.f[F_DIAG], i, j, k);
+        ln.lastT = t.f[F_DIAG].p[dof + TEMP * t.f[F_DIAG].nstride];
+        ln.lastNe = t.f[F_DIAG].p[dof + NE * t.f[F_DIAG].nstride];
         ln.rho_src = ln.rhoe_src = ln.e_src = ln.reset_src = 0.0; ln.zhi = 0.0;
         if (c.sdc_has_src) {
-            ln.rho_src = fab_at(t.f[F_HSRC], i, j, k, DENS) / c.dt;
-            ln.rhoe_src = fab_at(t.f[F_HSRC], i, j, k, EINT) / c.dt;
-            ln.reset_src = fab_at(t.f[F_RSRC], i, j, k, 0);
+            const long long ho = fab_off(t.f[F_HSRC], i, j, k);
+            ln.rho_src = t.f[F_HSRC].p[ho + DENS * t.f[F_HSRC].nstride] / c.dt;
+            ln.rhoe_src = t.f[F_HSRC].p[ho + EINT * t.f[F_HSRC].nstride] / c.dt;
+            ln.reset_src = t.f[F_RSRC].p[fab_off(t.f[F_RSRC], i, j, k)];
             ln.e_src = (((c.asq * rhoe0 + c.dt * ln.rhoe_src) / c.aendsq + ln.reset_src) / (ln.rho + c.dt * ln.rho_src) - ln.e0) / c.dt;
         }
-        if (c.inhomo) { ln.zhi = fab_at(t.f[F_DIAG], i, j, k, ZHI); ln.jh = (c.z > ln.zhi) ? 0.0 : 1.0; }
-        ln.rho_out = fab_at(t.f[F_SNEW], i, j, k, DENS);
-        ln.rhoe_new = fab_at(t.f[F_SNEW], i, j, k, EINT);
+        if (c.inhomo) { ln.zhi = t.f[F_DIAG].p[dof + ZHI * t.f[F_DIAG].nstride]; ln.jh = (c.z > ln.zhi) ? 0.0 : 1.0; }
+        const long long no = fab_off(t.f[F_SNEW], i, j, k);
+        ln.rho_out = t.f[F_SNEW].p[no + DENS * t.f[F_SNEW].nstride];
+        ln.rhoe_new = t.f[F_SNEW].p[no + EINT * t.f[F_SNEW].nstride];
+    } else {
+        ln.lastT = 0.0; ln.lastNe = 0.0;   // diag(Temp, Ne) are dead inputs on the Strang path (always overwritten, eos_hc.H:151)
     }
     ln.start(c);
 }
 
 // scatter a finished cell (HOT LOOP C: integrate_state_vec_3d.cpp:317-321, f_rhs_struct.H:290-291,438-444)
 template <int PATH>
-__device__ __forceinline__ void store_cell(const Lane<PATH>& ln, const KernelArgs& a, long long id, unsigned long long* sstats) {
-    const TileDesc& t = find_tile(a.tiles, a.ntiles, id);
-    int i, j, k; cell_ijk(t, id, i, j, k);
+__device__ __forceinline__ void store_cell(const KLane<PATH>& ln, const KernelArgs& a, const TileDesc& t, int i, int j, int k, Totals& tot) {
     const Consts& c = a.k;
-    fab_at(t.f[F_DIAG], i, j, k, TEMP) = ln.outT;
-    fab_at(t.f[F_DIAG], i, j, k, NE) = ln.outNe;
+    const long long dof = fab_off(t.f[F_DIAG], i, j, k);
+    t.f[F_DIAG].p[dof + TEMP * t.f[F_DIAG].nstride] = ln.outT;
+    t.f[F_DIAG].p[dof + NE * t.f[F_DIAG].nstride] = ln.outNe;
     if (PATH == PATH_VEC || !c.sdc_has_src) {
         const double d = ln.rho * (ln.e_final - ln.e0);
-        fab_at(t.f[F_STATE], i, j, k, EINT) += d;
-        fab_at(t.f[F_STATE], i, j, k, EDEN) += d;
+        double* ps = t.f[F_STATE].p + fab_off(t.f[F_STATE], i, j, k);
+        ps[EINT * t.f[F_STATE].nstride] += d;
+        ps[EDEN * t.f[F_STATE].nstride] += d;
     } else {
-        fab_at(t.f[F_IR], i, j, k, 0) = ln.IR;
+        t.f[F_IR].p[fab_off(t.f[F_IR], i, j, k)] = ln.IR;
         const double d = c.dt * c.ahalf * ln.IR / c.aendsq;
-        fab_at(t.f[F_SNEW], i, j, k, EINT) = ln.rhoe_new + d;
-        double& eden = fab_at(t.f[F_SNEW], i, j, k, EDEN);
-        eden = eden + d;
+        double* pn = t.f[F_SNEW].p + fab_off(t.f[F_SNEW], i, j, k);
+        pn[EINT * t.f[F_SNEW].nstride] = ln.rhoe_new + d;
+        pn[EDEN * t.f[F_SNEW].nstride] = pn[EDEN * t.f[F_SNEW].nstride] + d;
     }
-    if (a.cell_stats) a.cell_stats[id] = HcCellStat{ln.nst, ln.netf, ln.nfe, ln.nni, ln.nnf, ln.nsetups, ln.nfe_ls, ln.flag};
-    atomicAdd(&sstats[S_CELLS], 1ull);
-    if (ln.flag < 0) atomicAdd(&sstats[S_FAILED], 1ull);
-    if (ln.floor_hit) atomicAdd(&sstats[S_FLOOR], 1ull);
-    atomicAdd(&sstats[S_NST], (unsigned long long)ln.nst);
-    atomicMax(&sstats[S_MAXNST], (unsigned long long)ln.nst);
-    atomicAdd(&sstats[S_NFE], (unsigned long long)ln.nfe);
-    atomicAdd(&sstats[S_NFELS], (unsigned long long)ln.nfe_ls);
-    atomicAdd(&sstats[S_NETF], (unsigned long long)ln.netf);
-    atomicAdd(&sstats[S_NNI], (unsigned long long)ln.nni);
-    atomicAdd(&sstats[S_NCFN], (unsigned long long)ln.nnf);
-    atomicAdd(&sstats[S_NSETUPS], (unsigned long long)ln.nsetups);
-    atomicAdd(&sstats[S_NEITERS], (unsigned long long)ln.ne_iters);
-    atomicAdd(&sstats[S_ATTEMPTS], (unsigned long long)ln.attempts);
-    atomicAdd(&sstats[S_EOS], (unsigned long long)ln.n_eos);
+    if (a.cell_stats) {
+        const long long id = t.offset + ((long long)(k - t.lo[2]) * t.ny + (j - t.lo[1])) * t.nx + (i - t.lo[0]);
+        a.cell_stats[id] = HcCellStat{ln.nst, ln.netf, ln.nfe, ln.nni, ln.nnf, ln.nsetups, ln.nfe_ls, ln.flag};
+    }
+    tot.w[0] += 1ull | ((unsigned long long)(ln.flag < 0) << 32);
+    tot.w[1] += (unsigned long long)(unsigned)ln.floor_hit | ((unsigned long long)(unsigned)ln.nst << 32);
+    tot.w[2] += (unsigned long long)(unsigned)ln.nfe | ((unsigned long long)(unsigned)ln.nfe_ls << 32);
+    tot.w[3] += (unsigned long long)(unsigned)ln.netf | ((unsigned long long)(unsigned)ln.nni << 32);
+    tot.w[4] += (unsigned long long)(unsigned)ln.nnf | ((unsigned long long)(unsigned)ln.nsetups << 32);
+    tot.w[5] += (unsigned long long)(unsigned)ln.ne_iters | ((unsigned long long)(unsigned)ln.attempts << 32);
+    tot.w[6] += (unsigned long long)(unsigned)ln.n_eos;
+    tot.max_nst = max(tot.max_nst, (unsigned)ln.nst);
+}
+
+__device__ __forceinline__ void flush_totals(const Totals& tot, unsigned long long* s_stats, unsigned long long* dstats) {
+    // warp reduce (the packed halves cannot carry into each other: a lane integrates far fewer than 2^32 / 1e4 cells)
+    static const int lo_slot[7] = {S_CELLS, S_FLOOR, S_NFE, S_NETF, S_NCFN, S_NEITERS, S_EOS};
+    static const int hi_slot[7] = {S_FAILED, S_NST, S_NFELS, S_NNI, S_NSETUPS, S_ATTEMPTS, -1};
+#pragma unroll
+    for (int i = 0; i < 7; ++i) {
+        unsigned lo = (unsigned)(tot.w[i] & 0xffffffffull), hi = (unsigned)(tot.w[i] >> 32);
+        unsigned long long slo = lo, shi = hi;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { slo += __shfl_xor_sync(0xffffffffu, slo, o); shi += __shfl_xor_sync(0xffffffffu, shi, o); }
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd(&s_stats[lo_slot[i]], slo);
+            if (hi_slot[i] >= 0) atomicAdd(&s_stats[hi_slot[i]], shi);
+        }
+    }
+    unsigned mx = tot.max_nst;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(&s_stats[S_MAXNST], (unsigned long long)mx);
+    __syncthreads();
+    if (threadIdx.x < S_COUNT) {
+        if (threadIdx.x == S_MAXNST) atomicMax(&dstats[threadIdx.x], s_stats[threadIdx.x]);
+        else atomicAdd(&dstats[threadIdx.x], s_stats[threadIdx.x]);
+    }
 }
 
 template <int PATH>
 __global__ void __launch_bounds__(THREADS, 1) hc_integrate_kernel(const __grid_constant__ KernelArgs a) {
-    extern __shared__ __align__(16) double s_ion[];
     __shared__ unsigned long long s_stats[S_COUNT];
+    double* s_ionx = reinterpret_cast<double*>(s_raw);
+    double* s_iony = reinterpret_cast<double*>(s_raw + SM_IONX);
 
-    // stage the ionization tables (16-byte vector copies)
-    {
-        const double2* src = reinterpret_cast<const double2*>(a.ion);
-        double2* dst = reinterpret_cast<double2*>(s_ion);
-        for (int i = threadIdx.x; i < ION_ROWS * TABLE_ROW / 2; i += THREADS) dst[i] = __ldg(src + i);
-        if (threadIdx.x < S_COUNT) s_stats[threadIdx.x] = 0ull;
-    }
+    stage_tables(a, s_ionx, s_iony);
+    if (threadIdx.x < S_COUNT) s_stats[threadIdx.x] = 0ull;
     __syncthreads();
 
-    const Tables tb{s_ion, a.cool};
+    const Tables tb{s_ionx, s_iony, a.cool};
     const unsigned lane_id = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane_id) - 1u;
 
-    Lane<PATH> ln;
+    KLane<PATH> ln;
     ln.pc = PC_IDLE;
-    long long cell_id = -1;
+    ln.arr.p = reinterpret_cast<double*>(s_raw + SM_IONX + SM_IONY) + threadIdx.x;
+    Totals tot;
+#pragma unroll
+    for (int i = 0; i < 7; ++i) tot.w[i] = 0ull;
+    tot.max_nst = 0u;
+
+    // the warp's current chunk (warp-uniform) and the lane's current cell
+    int w_tile = 0, w_j = 0, w_k = 0, w_x = 0, w_xend = 0;
+    int c_tile = 0, c_i = 0, c_j = 0, c_k = 0;
     bool queue_empty = false;
 
     for (;;) {
-        // ---- refill free lanes from the global queue (warp-aggregated)
+        // ---- refill free lanes from the warp's chunk; pull a new chunk from the global queue when it is used up
         if (!queue_empty) {
-            const bool need = !ln.active();
-            const unsigned m = __ballot_sync(0xffffffffu, need);
-            if (m) {
-                const int cnt = __popc(m);
-                unsigned long long base = 0;
-                if (lane_id == 0) base = atomicAdd(a.queue, (unsigned long long)cnt);
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (base + cnt >= (unsigned long long)a.ncells) queue_empty = true;
-                if (need) {
-                    const long long id = (long long)(base + __popc(m & lt_mask));
-                    if (id < a.ncells) { cell_id = id; load_cell<PATH>(ln, a, id); }
+            bool need = !ln.active();
+            unsigned m = __ballot_sync(0xffffffffu, need);
+            while (m) {
+                if (w_x >= w_xend) {
+                    unsigned long long chunk = 0;
+                    if (lane_id == 0) chunk = atomicAdd(a.queue, 1ull);
+                    chunk = __shfl_sync(0xffffffffu, chunk, 0);
+                    if (chunk >= (unsigned long long)a.nchunks) { queue_empty = true; break; }
+                    w_tile = find_tile_by_chunk(a.tiles, a.ntiles, (long long)chunk);
+                    const TileDesc& t = a.tiles[w_tile];
+                    const unsigned local = (unsigned)((long long)chunk - t.chunk_begin);
+                    const unsigned row = local / (unsigned)t.cpr, piece = local - row * (unsigned)t.cpr;
+                    const unsigned kk = row / (unsigned)t.ny;
+                    w_k = t.lo[2] + (int)kk;
+                    w_j = t.lo[1] + (int)(row - kk * (unsigned)t.ny);
+                    w_x = t.lo[0] + (int)piece * t.chunk_len;
+                    w_xend = min(w_x + t.chunk_len, t.lo[0] + t.nx);
                 }
+                const int avail = w_xend - w_x;
+                const int rank = __popc(m & lt_mask);
+                if (need && rank < avail) {
+                    c_tile = w_tile; c_i = w_x + rank; c_j = w_j; c_k = w_k;
+                    load_cell<PATH>(ln, a, a.tiles[c_tile], c_i, c_j, c_k);
+                    // a cell whose integration cannot even start (illegal input) may be finished already: store it, stay free
+                    if (ln.active()) need = false;
+                    else store_cell<PATH>(ln, a, a.tiles[c_tile], c_i, c_j, c_k, tot);
+                }
+                w_x += min(avail, __popc(m));
+                m = __ballot_sync(0xffffffffu, need);
             }
         }
-        // a cell can complete inside start() only through the early-failure path, which still requests an EOS solve
-        if (!__any_sync(0xffffffffu, ln.active())) break;
+        const bool act0 = ln.active();
+        if (!__any_sync(0xffffffffu, act0)) break;   // nothing in flight and the refill found the queue empty
 
         // ---- all lanes evaluate their pending request together
         double f = 0.0;
-        if (ln.active()) f = ln.eval_request(tb, a.k);
+        if (act0) f = ln.eval_request(tb, a.k);
         __syncwarp();
-        // ---- integrator bookkeeping until the next request (cheap, divergent)
-        if (ln.active()) {
-            ln.resume(a.k, f);
-            if (!ln.active()) store_cell<PATH>(ln, a, cell_id, s_stats);
+        // ---- integrator bookkeeping until the next request (staged, see hc_device.cuh)
+        const unsigned rmask = __ballot_sync(0xffffffffu, act0);
+        if (act0) {
+            ln.resume(a.k, f, rmask);
+            if (!ln.active()) store_cell<PATH>(ln, a, a.tiles[c_tile], c_i, c_j, c_k, tot);
         }
         __syncwarp();
     }
 
-    __syncthreads();
-    if (threadIdx.x < S_COUNT) {
-        if (threadIdx.x == S_MAXNST) atomicMax(&a.dstats[threadIdx.x], s_stats[threadIdx.x]);
-        else atomicAdd(&a.dstats[threadIdx.x], s_stats[threadIdx.x]);
-    }
+    flush_totals(tot, s_stats, a.dstats);
 }
 
-// compute_new_temp core: one thread per cell, grid-stride; same table staging
+// compute_new_temp core: one thread per cell, grid-stride over x-rows; same table staging
 __global__ void __launch_bounds__(THREADS, 1) hc_eos_kernel(const __grid_constant__ KernelArgs a) {
-    extern __shared__ __align__(16) double s_ion[];
     __shared__ unsigned long long s_stats[S_COUNT];
-    {
-        const double2* src = reinterpret_cast<const double2*>(a.ion);
-        double2* dst = reinterpret_cast<double2*>(s_ion);
-        for (int i = threadIdx.x; i < ION_ROWS * TABLE_ROW / 2; i += THREADS) dst[i] = __ldg(src + i);
-        if (threadIdx.x < S_COUNT) s_stats[threadIdx.x] = 0ull;
-    }
+    double* s_ionx = reinterpret_cast<double*>(s_raw);
+    double* s_iony = reinterpret_cast<double*>(s_raw + SM_IONX);
+    stage_tables(a, s_ionx, s_iony);
+    if (threadIdx.x < S_COUNT) s_stats[threadIdx.x] = 0ull;
     __syncthreads();
-    const Tables tb{s_ion, a.cool};
+    const Tables tb{s_ionx, s_iony, a.cool};
     const Consts& c = a.k;
     unsigned long long iters = 0, cells = 0;
+    const TileDesc& t = a.tiles[0];
+    const long long plane = (long long)t.nx * t.ny;
     for (long long id = (long long)blockIdx.x * THREADS + threadIdx.x; id < a.ncells; id += (long long)gridDim.x * THREADS) {
-        const TileDesc& t = find_tile(a.tiles, a.ntiles, id);
-        int i, j, k; cell_ijk(t, id, i, j, k);
-        const double R = fab_at(t.f[F_STATE], i, j, k, DENS);
-        const double e = fab_at(t.f[F_STATE], i, j, k, EINT) / R;
+        const int kk = (int)(id / plane);
+        const int rem = (int)(id - (long long)kk * plane);
+        const int jj = rem / t.nx;
+        const int i = t.lo[0] + (rem - jj * t.nx), j = t.lo[1] + jj, k = t.lo[2] + kk;
+        const long long so = fab_off(t.f[F_STATE], i, j, k), dof = fab_off(t.f[F_DIAG], i, j, k);
+        const double R = t.f[F_STATE].p[so + DENS * t.f[F_STATE].nstride];
+        const double e = t.f[F_STATE].p[so + EINT * t.f[F_STATE].nstride] / R;
         const double rho_cgs = R * density_to_cgs / c.a3_eos;
         const double U = e * e_to_cgs;
         const double nh = rho_cgs * c.h_species / MPROTON;
         EosOut s;
         iterate_ne(tb, c, c.uvb_eos, 1.0, 1.0, U, nh, s);
-        fab_at(t.f[F_DIAG], i, j, k, TEMP) = s.T;
-        fab_at(t.f[F_DIAG], i, j, k, NE) = s.ne;
+        t.f[F_DIAG].p[dof + TEMP * t.f[F_DIAG].nstride] = s.T;
+        t.f[F_DIAG].p[dof + NE * t.f[F_DIAG].nstride] = s.ne;
         iters += s.iters; cells++;
     }
     atomicAdd(&s_stats[S_CELLS], cells);
@@ -263,7 +340,8 @@ void set_err(const char* fmt, ...) {
 #define CUDA_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { set_err("%s: %s (%s:%d)", #x, cudaGetErrorString(e_), __FILE__, __LINE__); return HC_ERR_CUDA; } } while (0)
 
 struct DeviceTables {
-    double* ion = nullptr;
+    double* ionx = nullptr;
+    double* iony = nullptr;
     double* cool = nullptr;
     int sm_count = 0;
     bool attr_set[3] = {false, false, false};
@@ -282,12 +360,18 @@ bool valid_params(const HcParams* p) {
     return p && p->rtol > 0.0 && p->atol_factor >= 0.0 && p->h_species > 0.0 && p->h_species <= 1.0;
 }
 
-TileDesc make_tile(const HcFab* const* fabs, int nf, int idx, const HcBox& b, long long offset) {
+TileDesc make_tile(const HcFab* const* fabs, int nf, int idx, const HcBox& b, long long offset, long long chunk_begin) {
     TileDesc t{};
     for (int s = 0; s < nf; ++s) t.f[s] = fabs[s][idx];
     for (int d = 0; d < 3; ++d) t.lo[d] = b.lo[d];
     t.nx = b.hi[0] - b.lo[0] + 1; t.ny = b.hi[1] - b.lo[1] + 1; t.nz = b.hi[2] - b.lo[2] + 1;
     t.offset = offset;
+    t.chunk_begin = chunk_begin;
+    if (t.nx > 0) {
+        // a chunk is a piece of one x-row: rows longer than CHUNK_MAX are cut into equal pieces
+        t.cpr = (t.nx + CHUNK_MAX - 1) / CHUNK_MAX;
+        t.chunk_len = (t.nx + t.cpr - 1) / t.cpr;
+    }
     return t;
 }
 
@@ -302,9 +386,9 @@ bool tile_inside(const TileDesc& t, int nf) {
 }
 
 template <typename KernelT>
-int set_smem_attr(KernelT kernel, DeviceTables& dt, int slot) {
+int set_smem_attr(KernelT kernel, DeviceTables& dt, int slot, size_t bytes) {
     if (!dt.attr_set[slot]) {
-        CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ION_SMEM_BYTES));
+        CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
         dt.attr_set[slot] = true;
     }
     return HC_OK;
@@ -315,15 +399,16 @@ int launch(int path, int ntiles, const HcFab* const* fabs, int nf, const HcBox* 
            HcCellStat* cell_stats, cudaStream_t stream) {
     int dev; if (int rc = current_device(dev)) return rc;
     DeviceTables& dt = g_dev[dev];
-    if (!dt.ion) { set_err("hc_tables_upload has not been called on device %d", dev); return HC_ERR_NO_TABLES; }
+    if (!dt.ionx) { set_err("hc_tables_upload has not been called on device %d", dev); return HC_ERR_NO_TABLES; }
     if (ntiles < 0) { set_err("ntiles < 0"); return HC_ERR_ARG; }
     std::vector<TileDesc> h_tiles; h_tiles.reserve(ntiles);
-    long long ncells = 0;
+    long long ncells = 0, nchunks = 0;
     for (int t = 0; t < ntiles; ++t) {
-        TileDesc td = make_tile(fabs, nf, t, tiles[t], ncells);
+        TileDesc td = make_tile(fabs, nf, t, tiles[t], ncells, nchunks);
         if (td.nx <= 0 || td.ny <= 0 || td.nz <= 0) continue;   // empty tile: nothing to do (as an empty MFIter tile)
         if (!tile_inside(td, nf)) { set_err("tile %d is not contained in its FABs (or a FAB pointer is null)", t); return HC_ERR_ARG; }
         ncells += (long long)td.nx * td.ny * td.nz;
+        nchunks += (long long)td.cpr * td.ny * td.nz;
         h_tiles.push_back(td);
     }
     if (stats) std::memset(stats, 0, sizeof *stats);
@@ -341,22 +426,23 @@ int launch(int path, int ntiles, const HcFab* const* fabs, int nf, const HcBox* 
     a.tiles = reinterpret_cast<const TileDesc*>(scratch + 256);
     a.ntiles = (int)h_tiles.size();
     a.ncells = ncells;
+    a.nchunks = nchunks;
     a.queue = reinterpret_cast<unsigned long long*>(scratch);
     a.dstats = reinterpret_cast<unsigned long long*>(scratch + 64);
     a.cell_stats = cell_stats;
-    a.ion = dt.ion; a.cool = dt.cool;
+    a.ionx = dt.ionx; a.iony = dt.iony; a.cool = dt.cool;
 
     const long long want = (ncells + THREADS - 1) / THREADS;
     const int grid = (int)std::min<long long>(want, dt.sm_count);
     if (path == PATH_VEC) {
-        if (int rc = set_smem_attr(hc_integrate_kernel<PATH_VEC>, dt, 0)) return rc;
-        hc_integrate_kernel<PATH_VEC><<<grid, THREADS, ION_SMEM_BYTES, stream>>>(a);
+        if (int rc = set_smem_attr(hc_integrate_kernel<PATH_VEC>, dt, 0, SMEM_INTEGRATE)) return rc;
+        hc_integrate_kernel<PATH_VEC><<<grid, THREADS, SMEM_INTEGRATE, stream>>>(a);
     } else if (path == PATH_STRUCT) {
-        if (int rc = set_smem_attr(hc_integrate_kernel<PATH_STRUCT>, dt, 1)) return rc;
-        hc_integrate_kernel<PATH_STRUCT><<<grid, THREADS, ION_SMEM_BYTES, stream>>>(a);
+        if (int rc = set_smem_attr(hc_integrate_kernel<PATH_STRUCT>, dt, 1, SMEM_INTEGRATE)) return rc;
+        hc_integrate_kernel<PATH_STRUCT><<<grid, THREADS, SMEM_INTEGRATE, stream>>>(a);
     } else {
-        if (int rc = set_smem_attr(hc_eos_kernel, dt, 2)) return rc;
-        hc_eos_kernel<<<grid, THREADS, ION_SMEM_BYTES, stream>>>(a);
+        if (int rc = set_smem_attr(hc_eos_kernel, dt, 2, SMEM_EOS)) return rc;
+        hc_eos_kernel<<<grid, THREADS, SMEM_EOS, stream>>>(a);
     }
     CUDA_TRY(cudaGetLastError());
     if (stats) {
@@ -429,15 +515,17 @@ int hc_tables_upload(const double* rates, size_t n_doubles) {
     int dev; if (int rc = current_device(dev)) return rc;
     std::lock_guard<std::mutex> lock(g_mu);
     g_rates.assign(rates, rates + n_doubles);
-    std::vector<double> ion, cool;
-    interleave_tables(rates, ion, cool);
+    std::vector<double> ionx, iony, cool;
+    interleave_tables(rates, ionx, iony, cool);
     DeviceTables& dt = g_dev[dev];
-    if (!dt.ion) {
-        CUDA_TRY(cudaMalloc((void**)&dt.ion, ion.size() * sizeof(double)));
+    if (!dt.ionx) {
+        CUDA_TRY(cudaMalloc((void**)&dt.ionx, ionx.size() * sizeof(double)));
+        CUDA_TRY(cudaMalloc((void**)&dt.iony, iony.size() * sizeof(double)));
         CUDA_TRY(cudaMalloc((void**)&dt.cool, cool.size() * sizeof(double)));
         CUDA_TRY(cudaDeviceGetAttribute(&dt.sm_count, cudaDevAttrMultiProcessorCount, dev));
     }
-    CUDA_TRY(cudaMemcpy(dt.ion, ion.data(), ion.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(dt.ionx, ionx.data(), ionx.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(dt.iony, iony.data(), iony.size() * sizeof(double), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(dt.cool, cool.data(), cool.size() * sizeof(double), cudaMemcpyHostToDevice));
     return HC_OK;
 }

@@ -9,6 +9,11 @@
 using namespace hc;
 
 namespace {
+// array storage policy of the lane on the host: one lane at a time, a plain static array
+struct ArrHost {
+    double a[ARR_DOUBLES];
+    double& at(int slot) { return a[slot]; }
+};
 struct View {
     double* p; long long js, ks, ns; int lo[3];
     double& operator()(int i, int j, int k, int n) const { return p[(i - lo[0]) + (j - lo[1]) * js + (k - lo[2]) * ks + n * ns]; }
@@ -26,21 +31,21 @@ int hh_tabulate_rates(const char* file, double mean_rhob, double* out) { return 
 
 int hh_integrate_vec(const double* rates, const HcParams* prm, const HcFab* state, const HcFab* diag, HcBox tile, double a, double dt,
                      HcCellStat* cs) {
-    std::vector<double> ion, cool;
-    interleave_tables(rates, ion, cool);
-    Tables tb{ion.data(), cool.data()};
+    std::vector<double> ionx, iony, cool;
+    interleave_tables(rates, ionx, iony, cool);
+    Tables tb{ionx.data(), iony.data(), cool.data()};
     const Consts k = make_consts_vec(rates, *prm, a, dt);
     View S = view(state), D = view(diag);
     long idx = 0;
     for (int kk = tile.lo[2]; kk <= tile.hi[2]; ++kk) for (int j = tile.lo[1]; j <= tile.hi[1]; ++j) for (int i = tile.lo[0]; i <= tile.hi[0]; ++i, ++idx) {
-        Lane<PATH_VEC> ln;
+        Lane<PATH_VEC, ArrHost> ln;
         ln.rho = S(i, j, kk, 0);
         ln.e0 = S(i, j, kk, 5) / ln.rho;
         ln.abstol = nv_scale(k.atol_factor, ln.e0);
         ln.jh = 1.0;
         ln.lastT = D(i, j, kk, 0); ln.lastNe = D(i, j, kk, 1);
         ln.start(k);
-        while (ln.active()) { const double f = ln.eval_request(tb, k); ln.resume(k, f); }
+        while (ln.active()) { const double f = ln.eval_request(tb, k); ln.resume(k, f, 0u); }
         D(i, j, kk, 0) = ln.outT; D(i, j, kk, 1) = ln.outNe;
         S(i, j, kk, 5) += S(i, j, kk, 0) * (ln.e_final - ln.e0);
         S(i, j, kk, 4) += S(i, j, kk, 0) * (ln.e_final - ln.e0);
@@ -52,14 +57,14 @@ int hh_integrate_vec(const double* rates, const HcParams* prm, const HcFab* stat
 int hh_integrate_struct(const double* rates, const HcParams* prm, const HcFab* s_old, const HcFab* diag, const HcFab* s_new,
                         const HcFab* hydro_src, const HcFab* reset_src, const HcFab* ir, HcBox tile, double a, double a_end, double dt,
                         int sdc_iter, HcCellStat* cs) {
-    std::vector<double> ion, cool;
-    interleave_tables(rates, ion, cool);
-    Tables tb{ion.data(), cool.data()};
+    std::vector<double> ionx, iony, cool;
+    interleave_tables(rates, ionx, iony, cool);
+    Tables tb{ionx.data(), iony.data(), cool.data()};
     const Consts k = make_consts_struct(rates, *prm, a, a_end, dt, sdc_iter);
     View S = view(s_old), D = view(diag), N = view(s_new), H = view(hydro_src), R = view(reset_src), I = view(ir);
     long idx = 0;
     for (int kk = tile.lo[2]; kk <= tile.hi[2]; ++kk) for (int j = tile.lo[1]; j <= tile.hi[1]; ++j) for (int i = tile.lo[0]; i <= tile.hi[0]; ++i, ++idx) {
-        Lane<PATH_STRUCT> ln;
+        Lane<PATH_STRUCT, ArrHost> ln;
         ln.rho = S(i, j, kk, 0);
         const double rhoe0 = S(i, j, kk, 5);
         ln.e0 = rhoe0 / ln.rho;
@@ -76,7 +81,7 @@ int hh_integrate_struct(const double* rates, const HcParams* prm, const HcFab* s
         if (k.inhomo) { ln.zhi = D(i, j, kk, 2); ln.jh = (k.z > ln.zhi) ? 0.0 : 1.0; }
         ln.rho_out = N(i, j, kk, 0); ln.rhoe_new = N(i, j, kk, 5);
         ln.start(k);
-        while (ln.active()) { const double f = ln.eval_request(tb, k); ln.resume(k, f); }
+        while (ln.active()) { const double f = ln.eval_request(tb, k); ln.resume(k, f, 0u); }
         D(i, j, kk, 0) = ln.outT; D(i, j, kk, 1) = ln.outNe;
         if (k.sdc_has_src) {
             I(i, j, kk, 0) = ln.IR;
