@@ -21,15 +21,42 @@
 #include <mutex>
 #include <vector>
 
+// Build-time tuning knobs (measured on B200, profiles/): 384 lanes per SM leave 168 registers per lane (the integrator state
+// stays in registers), and the CTA-wide phase lock keeps one phase's code in the small instruction caches at a time.
+#ifndef HC_LOCKSTEP
+#define HC_LOCKSTEP 1                      // 0: warps free-run; 1: CTA-wide RHS / bookkeeping phase lock; 2: per-scheduler warp groups in lockstep
+#endif
+#ifndef HC_THREADS
+#define HC_THREADS 384                     // lanes (cells in flight) per SM; one persistent CTA per SM
+#endif
+#if HC_LOCKSTEP == 2
+// SMSP-group lockstep: the warps that share a scheduler (warp id mod 4) -- and with it an L0 instruction cache -- step through
+// the RHS evaluation points and the bookkeeping stages together, synchronised by a named barrier per group.
+__host__ __device__ __forceinline__ void hc_group_sync() {
+#if defined(__CUDA_ARCH__)
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + (int)((threadIdx.x >> 5) & 3u)), "r"(HC_THREADS / 4) : "memory");
+#endif
+}
+__host__ __device__ __forceinline__ bool hc_group_all(bool pred) {
+#if defined(__CUDA_ARCH__)
+    int r;
+    asm volatile("{ .reg .pred p, q; setp.ne.s32 q, %3, 0; bar.red.and.pred p, %1, %2, q; selp.s32 %0, 1, 0, p; }"
+                 : "=r"(r) : "r"(1 + (int)((threadIdx.x >> 5) & 3u)), "r"(HC_THREADS / 4), "r"((int)pred) : "memory");
+    return r != 0;
+#else
+    return pred;
+#endif
+}
+#define HC_STAGE_SYNC(mask, act) do { hc_group_sync(); asm volatile("" : "+r"(act)); } while (0)
+#define HC_GROUP_ALL(pred) hc_group_all(pred)
+#define HC_GROUP_RHS 1
+#endif
 #include "hc_host.hpp"
 
 namespace {
 
 using namespace hc;
 
-#ifndef HC_THREADS
-#define HC_THREADS 512                     // lanes (cells in flight) per SM; one persistent CTA per SM
-#endif
 constexpr int THREADS = HC_THREADS;
 constexpr int TAB_ROWS = NTAB + 1;         // one padding row: row j+1 always exists
 constexpr int CHUNK_MAX = 256;             // cells per work-queue chunk (a piece of one x-row of a tile)
@@ -175,25 +202,17 @@ __device__ __forceinline__ void store_cell(const KLane<PATH>& ln, const KernelAr
     tot.max_nst = max(tot.max_nst, (unsigned)ln.nst);
 }
 
-__device__ __forceinline__ void flush_totals(const Totals& tot, unsigned long long* s_stats, unsigned long long* dstats) {
-    // warp reduce (the packed halves cannot carry into each other: a lane integrates far fewer than 2^32 / 1e4 cells)
-    static const int lo_slot[7] = {S_CELLS, S_FLOOR, S_NFE, S_NETF, S_NCFN, S_NEITERS, S_EOS};
-    static const int hi_slot[7] = {S_FAILED, S_NST, S_NFELS, S_NNI, S_NSETUPS, S_ATTEMPTS, -1};
-#pragma unroll
+__device__ __noinline__ void flush_totals(const Totals& tot, unsigned long long* s_stats, unsigned long long* dstats) {
+    // once per thread at the end of the kernel: shared-memory atomics, then one global atomic per counter per CTA
+    const int lo_slot[7] = {S_CELLS, S_FLOOR, S_NFE, S_NETF, S_NCFN, S_NEITERS, S_EOS};
+    const int hi_slot[7] = {S_FAILED, S_NST, S_NFELS, S_NNI, S_NSETUPS, S_ATTEMPTS, -1};
+#pragma unroll 1
     for (int i = 0; i < 7; ++i) {
-        unsigned lo = (unsigned)(tot.w[i] & 0xffffffffull), hi = (unsigned)(tot.w[i] >> 32);
-        unsigned long long slo = lo, shi = hi;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { slo += __shfl_xor_sync(0xffffffffu, slo, o); shi += __shfl_xor_sync(0xffffffffu, shi, o); }
-        if ((threadIdx.x & 31) == 0) {
-            atomicAdd(&s_stats[lo_slot[i]], slo);
-            if (hi_slot[i] >= 0) atomicAdd(&s_stats[hi_slot[i]], shi);
-        }
+        const unsigned long long lo = tot.w[i] & 0xffffffffull, hi = tot.w[i] >> 32;
+        if (lo) atomicAdd(&s_stats[lo_slot[i]], lo);
+        if (hi && hi_slot[i] >= 0) atomicAdd(&s_stats[hi_slot[i]], hi);
     }
-    unsigned mx = tot.max_nst;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    if ((threadIdx.x & 31) == 0) atomicMax(&s_stats[S_MAXNST], (unsigned long long)mx);
+    atomicMax(&s_stats[S_MAXNST], (unsigned long long)tot.max_nst);
     __syncthreads();
     if (threadIdx.x < S_COUNT) {
         if (threadIdx.x == S_MAXNST) atomicMax(&dstats[threadIdx.x], s_stats[threadIdx.x]);
@@ -217,6 +236,7 @@ __global__ void __launch_bounds__(THREADS, 1) hc_integrate_kernel(const __grid_c
 
     KLane<PATH> ln;
     ln.pc = PC_IDLE;
+    ln.rho = 1.0e10; ln.req_y = 200.0; ln.req_t = 0.0; ln.jh = 1.0; ln.rho_src = 0.0; ln.e_src = 0.0; ln.lastRho = 1.0e10;   // benign idle request
     ln.arr.p = reinterpret_cast<double*>(s_raw + SM_IONX + SM_IONY) + threadIdx.x;
     Totals tot;
 #pragma unroll
@@ -263,18 +283,34 @@ __global__ void __launch_bounds__(THREADS, 1) hc_integrate_kernel(const __grid_c
             }
         }
         const bool act0 = ln.active();
+#if HC_LOCKSTEP
+        // CTA-wide phase lock: all warps of the SM run the RHS code together, then the bookkeeping code together, so that
+        // the instruction caches hold one phase's code at a time
+        if (!__syncthreads_or(act0)) break;
+#else
         if (!__any_sync(0xffffffffu, act0)) break;   // nothing in flight and the refill found the queue empty
+#endif
 
         // ---- all lanes evaluate their pending request together
         double f = 0.0;
+#if HC_LOCKSTEP == 2
+        f = ln.eval_request(tb, a.k);          // idle lanes evaluate a benign request: every lane takes part in the group barriers
+        ln.resume(a.k, f, 0xffffffffu);        // (an idle lane falls through all stages)
+        if (act0 && !ln.active()) store_cell<PATH>(ln, a, a.tiles[c_tile], c_i, c_j, c_k, tot);
+#else
         if (act0) f = ln.eval_request(tb, a.k);
+#if HC_LOCKSTEP
+        __syncthreads();
+#else
         __syncwarp();
+#endif
         // ---- integrator bookkeeping until the next request (staged, see hc_device.cuh)
         const unsigned rmask = __ballot_sync(0xffffffffu, act0);
         if (act0) {
             ln.resume(a.k, f, rmask);
             if (!ln.active()) store_cell<PATH>(ln, a, a.tiles[c_tile], c_i, c_j, c_k, tot);
         }
+#endif
         __syncwarp();
     }
 

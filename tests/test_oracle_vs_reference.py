@@ -1,0 +1,100 @@
+"""The oracle's C restatement against the REFERENCE ITSELF (oracle/_ref: Nyx HeatCool sources + SUNDIALS CVODE compiled from
+/root/reference by oracle/Makefile), bit for bit.  Skipped where oracle/_ref is not built (then tests/test_oracle_golden.py,
+which holds outputs of the same reference build, still pins the oracle)."""
+import numpy as np
+import pytest
+
+from nyx_b200 import synth
+from tests import util
+
+
+def test_tables_and_uvb(reference, port):
+    assert np.array_equal(reference.rates(), port.rates())
+    from oracle import pyref
+    for z in (0.0, 1.7, 2.999, 3.0, 6.0, 14.99, 20.0):
+        a, b = np.zeros(6), np.zeros(6)
+        reference.lib.nyxref_interp_to_this_z(float(z), a.ctypes.data_as(pyref._dp))
+        port.lib.hco_interp_to_this_z(port.rp, float(z), b.ctypes.data_as(pyref._dp))
+        assert np.array_equal(a, b), z
+
+
+def test_ion_n_and_eos_probes(reference, port):
+    rng = np.random.default_rng(3)
+    for _ in range(2000):
+        U = 10.0 ** rng.uniform(9.0, 16.0)
+        nh = 10.0 ** rng.uniform(-8.0, -1.0)
+        ne = 10.0 ** rng.uniform(-6.0, 0.1)
+        z = rng.choice([2.0, 3.0, 6.0, 9.0, 16.0])
+        JH, JHe = int(rng.integers(0, 2)), int(rng.integers(0, 2))
+        assert np.array_equal(reference.ion_n(JH, JHe, U, nh, ne, 2.0 / 3.0, 0.76, z), port.ion_n(JH, JHe, U, nh, ne, 2.0 / 3.0, 0.76, z))
+    for _ in range(500):
+        R = synth.mean_rhob() * np.exp(rng.normal(0, 2.0))
+        e = synth.e_from_T(10.0 ** rng.uniform(0.5, 9.5))
+        a = 1.0 / (1.0 + rng.uniform(1.5, 8.0))
+        assert reference.eos_T_given_Re(1, 1, float(R), float(e), float(a), 2.0 / 3.0, 0.76) == port.eos_T_given_Re(1, 1, float(R), float(e), float(a), 2.0 / 3.0, 0.76)
+
+
+@pytest.mark.parametrize("z,n,seed", [(3.0, 10, 301), (2.0, 10, 302), (6.0, 10, 303)])
+def test_vec_percell_mode_bitwise(reference, port, z, n, seed):
+    a, dt = 1.0 / (1.0 + z), 0.5 * synth.step_dt(z)
+    state, diag = synth.make_fab((n, n, n), seed=seed, z=z)
+    lo, hi = (0, 0, 0), (n - 1, n - 1, n - 1)
+    s1, d1 = state.copy(), diag.copy()
+    reference.set("nyx.sundials_tile_size", "1 1 1")
+    reference.stats_reset()
+    try:
+        reference.integrate_state_vec([lo + hi], [s1], [d1], a, dt)
+    finally:
+        reference.set("nyx.sundials_tile_size", "1024000 8 8")
+    pst = port.integrate_state_vec(state, diag, lo, hi, a, dt)
+    assert np.array_equal(s1, state) and np.array_equal(d1, diag)
+    assert np.array_equal(reference.stats(), pst[:, :8])
+
+
+def test_grownvec_ghost_cells_integrated(reference, port):
+    """integrate_state_grownvec (HC/integrate_state_vec_3d.cpp:367-396) integrates the ghost cells too."""
+    z, n, ng = 3.0, 6, 2
+    a, dt = 1.0 / (1.0 + z), 0.5 * synth.step_dt(z)
+    m = n + 2 * ng
+    state, diag = synth.make_fab((m, m, m), seed=311, z=z)
+    lo, hi = (0, 0, 0), (n - 1, n - 1, n - 1)
+    s1, d1 = state.copy(), diag.copy()
+    reference.set("nyx.sundials_tile_size", "1 1 1")
+    try:
+        reference.integrate_state_vec([lo + hi], [s1], [d1], a, dt, ng_state=ng, ng_diag=ng, grown=True)
+    finally:
+        reference.set("nyx.sundials_tile_size", "1024000 8 8")
+    glo, ghi = (-ng,) * 3, (n - 1 + ng,) * 3
+    orig = state.copy()
+    port.integrate_state_vec(state, diag, glo, ghi, a, dt, fab_lo=glo)
+    assert np.all(s1[5] != orig[5]) and np.all(state[5] != orig[5])           # every ghost cell was integrated by both
+    # with tile size 1 the reference's EDGE tiles are grown (1+ng cells wide: one coupled CVODE instance), the interior tiles
+    # are single cells: interior bit-identical, edge/ghost region within the 10 x rtol contract
+    inner = (slice(ng + 1, m - ng - 1),) * 3
+    assert np.array_equal(s1[5][inner], state[5][inner]) and np.array_equal(d1[0][inner], diag[0][inner])
+    assert np.abs(s1[5] / state[5] - 1).max() < 1e-3 and np.abs(d1[0] / diag[0] - 1).max() < 1e-3
+
+
+@pytest.mark.parametrize("z,seed,src,flash", [(2.0, 322, 0.05, "none"), (5.99, 324, 0.05, "hi_now"), (3.0, 325, 0.05, "heii_now")])
+def test_struct_percell_mode_bitwise(reference, port, z, seed, src, flash):
+    from tests.golden.make_golden import FLASH_KEYS
+    n = 8
+    d = util.sdc_inputs(z, n, seed, src)
+    r = {k: (v.copy() if hasattr(v, "copy") else v) for k, v in d.items()}
+    lo, hi = (0, 0, 0), (n - 1, n - 1, n - 1)
+    reference.set("nyx.sundials_tile_size", "1 1 1")
+    for k, v in util.FLASH_CASES[flash].items():
+        reference.set(FLASH_KEYS[k], v)
+    reference.stats_reset()
+    try:
+        reference.integrate_state_struct([lo + hi], [r["s_old"]], [r["s_new"]], [r["diag"]], [r["hydro_src"]], [r["ir"]], [r["reset_src"]],
+                                         d["a"], d["a_end"], d["dt"], 0)
+    finally:
+        reference.set("nyx.sundials_tile_size", "1024000 8 8")
+        for k in util.FLASH_CASES[flash]:
+            reference.unset(FLASH_KEYS[k])
+    pst = port.integrate_state_struct(d["s_old"], d["s_new"], d["diag"], d["hydro_src"], d["reset_src"], d["ir"], lo, hi,
+                                      d["a"], d["a_end"], d["dt"], 0, params=port.params(**util.FLASH_CASES[flash]))
+    for k in ("s_old", "s_new", "diag", "ir"):
+        assert np.array_equal(d[k], r[k]), k
+    assert np.array_equal(reference.stats(), pst[:, :8])

@@ -62,18 +62,17 @@ print(f"total samples {tot[0]}  warp-inst {tot[1]}  avg active threads {tot[2] /
 for key, a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
     st = ", ".join(f"{k[6:]}={v}" for k, v in sorted(a[3].items(), key=lambda kv: -kv[1])[:4])
     print(f"{key[0]}:{key[1]:<5d} samples {a[0]:7d} ({100 * a[0] / tot[0]:5.1f}%)  inst {a[1]:11d} ({100 * a[1] / tot[1]:5.1f}%)  act {a[2] / max(a[1], 1):5.1f}  {st}")
-# ---- region summary (hc_device.cuh line ranges)
-regions = [("ion_n/iterate_ne", "hc_device.cuh", 127, 197), ("rhs_tail", "hc_device.cuh", 198, 241), ("eval_request", "hc_device.cuh", 309, 349),
-           ("helpers nv_*/pow", "hc_device.cuh", 100, 126), ("lane bookkeeping", "hc_device.cuh", 250, 308), ("lane bookkeeping", "hc_device.cuh", 350, 860),
-           ("kernel shell", "nyx_hc.cu", 0, 10**6)]
-ra = defaultdict(lambda: [0, 0, 0])
+# ---- per-function summary (tools/regions.py maps file:line to the enclosing function / resume() stage)
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from regions import region
+root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ra = defaultdict(lambda: [0, 0, 0, defaultdict(int)])
 for key, a in agg.items():
-    name = "other (" + key[0] + ")"
-    for nm, f, lo, hi in regions:
-        if key[0] == f and lo <= key[1] <= hi:
-            name = nm
-            break
+    name = region(root, key[0], key[1])
     ra[name][0] += a[0]; ra[name][1] += a[1]; ra[name][2] += a[2]
-print("---- regions")
-for nm, a in sorted(ra.items(), key=lambda kv: -kv[1][1]):
-    print(f"{nm:28s} samples {100 * a[0] / tot[0]:5.1f}%  warp-inst {100 * a[1] / tot[1]:5.1f}%  thread-inst {100 * a[2] / tot[2]:5.1f}%  act {a[2] / max(a[1], 1):5.1f}")
+    for k2, v2 in a[3].items():
+        ra[name][3][k2] += v2
+print("---- functions (source files as they are NOW: re-run right after profiling)")
+for nm, a in sorted(ra.items(), key=lambda kv: -kv[1][1])[:45]:
+    st = ", ".join(f"{k[6:]}={100 * v / max(a[0], 1):.0f}%" for k, v in sorted(a[3].items(), key=lambda kv: -kv[1])[:4])
+    print(f"{nm:44s} samples {100 * a[0] / tot[0]:5.1f}%  warp-inst {100 * a[1] / tot[1]:5.1f}%  act {a[2] / max(a[1], 1):5.1f}  {st}")
