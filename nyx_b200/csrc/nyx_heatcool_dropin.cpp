@@ -1,0 +1,183 @@
+// nyx_heatcool_dropin.cpp -- host side of the B200 HeatCool path: the definitions of
+//
+//     Nyx::integrate_state_vec        Nyx::integrate_state_grownvec      Nyx::integrate_state_vec_mfin
+//     Nyx::integrate_state_struct     Nyx::integrate_state_struct_mfin
+//
+// with the reference's exact signatures (Source/Driver/Nyx.H:549-580).  This translation unit REPLACES
+// Source/HeatCool/integrate_state_vec_3d.cpp and integrate_state_with_source_3d.cpp in a Nyx build, the same way the
+// reference's *_stubs.cpp files replace them (Source/HeatCool/Make.package:11-22); the callers strang_first_step /
+// strang_second_step / sdc_reactions / advance_heatcool compile unchanged.  No SUNDIALS, no AMReX ParallelFor: the MFIter
+// loop only COLLECTS Array4 views, and one C-ABI call (include/nyx_hc.h) integrates all local boxes in one persistent launch.
+//
+// Differences a maintainer should know:
+//   * every cell is integrated by its own BDF instance (== the reference run with nyx.sundials_tile_size = 1 1 1): the
+//     CVODE tile size and nyx.sundials_use_tiling no longer influence results;
+//   * the CVode flag the reference ignores (integrate_state_vec_3d.cpp:284) is counted per cell (nyx_hc_last_stats());
+//   * nyx.use_sundials_fused / sundials_alloc_type / sundials_atomic_reductions are accepted and ignored;
+//   * FAB memory must be device-accessible when AMReX is built with AMREX_USE_GPU; in a CPU build of AMReX the host-buffer
+//     entry points stage the touched components through pinned memory.
+#include <AMReX_MultiFab.H>
+#include <AMReX_ParmParse.H>
+#include <Nyx.H>
+
+#include <algorithm>
+#include <vector>
+
+#include "nyx_hc.h"
+
+using namespace amrex;
+
+namespace {
+
+HcStats g_last_stats;   // diagnostics of the most recent call on this rank
+
+HcFab to_fab(Array4<Real> const& a) {
+    HcFab f{};
+    f.p = a.p;
+    f.jstride = a.jstride; f.kstride = a.kstride; f.nstride = a.nstride;
+    f.lo[0] = a.begin.x; f.lo[1] = a.begin.y; f.lo[2] = a.begin.z;
+    f.hi[0] = a.end.x - 1; f.hi[1] = a.end.y - 1; f.hi[2] = a.end.z - 1;   // Array4::end is exclusive
+    f.ncomp = a.ncomp;
+    return f;
+}
+
+HcBox to_box(const Box& b) {
+    HcBox r;
+    for (int d = 0; d < 3; ++d) { r.lo[d] = b.smallEnd(d); r.hi[d] = b.bigEnd(d); }
+    return r;
+}
+
+// the nyx.* run-time flags of the path: Nyx statics (Source/Driver/Nyx.cpp:116-181) + what ode_eos_setup re-parses on every
+// tile call in the reference (Source/HeatCool/f_rhs_struct.H:45-101); parsed once per call here
+HcParams params_from_nyx(long int old_max_steps) {
+    HcParams p;
+    hc_default_params(&p);
+    p.rtol = Nyx::sundials_reltol;
+    p.atol_factor = Nyx::sundials_abstol;
+    p.h_species = Nyx::h_species;
+    p.gamma_minus_1 = Nyx::gamma - 1.0;
+    p.max_steps = 2000;                               // CVodeSetMaxNumSteps(cvode_mem, 2000)
+    p.use_typical_steps = Nyx::use_typical_steps;
+    p.old_max_steps = old_max_steps;                  // CVodeSetMaxStep(cvode_mem, delta_time / old_max_steps)
+    p.use_constraint = Nyx::use_sundials_constraint;
+    ParmParse pp_nyx("nyx");
+    pp_nyx.query("inhomo_reion", p.inhomo_reion);
+    pp_nyx.query("uvb_density_A", p.uvb_density_A);
+    pp_nyx.query("uvb_density_B", p.uvb_density_B);
+    pp_nyx.query("reionization_zHI_flash", p.zhi_flash);
+    pp_nyx.query("reionization_zHeII_flash", p.zheii_flash);
+    pp_nyx.query("reionization_T_zHI", p.T_zhi);
+    pp_nyx.query("reionization_T_zHeII", p.T_zheii);
+    return p;
+}
+
+int check(int rc) {
+    if (rc != HC_OK) amrex::Abort(std::string("nyx_hc: ") + hc_last_error());
+    return 0;   // like the reference: per-cell integrator failures are not errors (they are counted in HcStats)
+}
+
+void finish(const HcStats& st, long int& new_max_steps) {
+    g_last_stats = st;
+    if (Nyx::use_typical_steps) new_max_steps = std::max<long int>(st.max_nst, new_max_steps);   // integrate_state_vec_3d.cpp:285-290
+}
+
+int vec_batch(std::vector<HcFab>& s, std::vector<HcFab>& d, std::vector<HcBox>& t, Real a, Real dt, long int old_max, long int& new_max) {
+    if (t.empty()) return 0;
+    const HcParams p = params_from_nyx(old_max);
+    HcStats st{};
+#ifdef AMREX_USE_GPU
+    const int rc = hc_integrate_vec_batch((int)t.size(), s.data(), d.data(), t.data(), a, dt, &p, &st, nullptr, nullptr);
+#else
+    const int rc = hc_integrate_vec_host((int)t.size(), s.data(), d.data(), t.data(), a, dt, &p, &st);
+#endif
+    finish(st, new_max);
+    return check(rc);
+}
+
+}  // namespace
+
+extern "C" const HcStats* nyx_hc_last_stats() { return &g_last_stats; }
+
+// Replaces the call `tabulate_rates(file_in, mean_rhob)` in Nyx::heatcool_setup (Source/Initialization/Nyx_setup.cpp:157-166):
+// builds the same AtomicRates image on the host and uploads it to the current device.
+extern "C" int nyx_hc_setup(const char* treecool_path, double mean_rhob)
+{
+    std::vector<double> rates(HC_RATES_DOUBLES);
+    int rc = hc_tabulate_rates(treecool_path, mean_rhob, rates.data());
+    if (rc == HC_OK) rc = hc_tables_upload(rates.data(), rates.size());
+    if (rc != HC_OK) amrex::Abort(std::string("nyx_hc_setup: ") + hc_last_error());
+    return rc;
+}
+
+// HC/integrate_state_vec_3d.cpp:44-70: valid cells of every local box
+int Nyx::integrate_state_vec(MultiFab& S_old, MultiFab& D_old, const Real& a, const Real& delta_time)
+{
+    const long int store_steps = new_max_sundials_steps;
+    std::vector<HcFab> s, d; std::vector<HcBox> t;
+    for (MFIter mfi(S_old); mfi.isValid(); ++mfi) {
+        s.push_back(to_fab(S_old.array(mfi))); d.push_back(to_fab(D_old.array(mfi))); t.push_back(to_box(mfi.validbox()));
+    }
+    return vec_batch(s, d, t, a, delta_time, store_steps, new_max_sundials_steps);
+}
+
+// HC/integrate_state_vec_3d.cpp:367-396: valid cells AND the ghost cells of S_old (growntilebox of an untiled MFIter)
+int Nyx::integrate_state_grownvec(MultiFab& S_old, MultiFab& D_old, const Real& a, const Real& delta_time)
+{
+    const long int store_steps = new_max_sundials_steps;
+    std::vector<HcFab> s, d; std::vector<HcBox> t;
+    for (MFIter mfi(S_old); mfi.isValid(); ++mfi) {
+        s.push_back(to_fab(S_old.array(mfi))); d.push_back(to_fab(D_old.array(mfi))); t.push_back(to_box(mfi.growntilebox()));
+    }
+    return vec_batch(s, d, t, a, delta_time, store_steps, new_max_sundials_steps);
+}
+
+// HC/integrate_state_vec_3d.cpp:72-365: one tile
+int Nyx::integrate_state_vec_mfin(Array4<Real> const& state4, Array4<Real> const& diag_eos4, const Box& tbx, const Real& a,
+                                  const Real& delta_time, long int& old_max_steps, long int& new_max_steps)
+{
+    std::vector<HcFab> s{to_fab(state4)}, d{to_fab(diag_eos4)}; std::vector<HcBox> t{to_box(tbx)};
+    return vec_batch(s, d, t, a, delta_time, old_max_steps, new_max_steps);
+}
+
+namespace {
+int struct_batch(std::vector<HcFab> f[6], std::vector<HcBox>& t, Real a, Real a_end, Real dt, int sdc_iter, long int old_max, long int& new_max) {
+    if (t.empty()) return 0;
+    const HcParams p = params_from_nyx(old_max);
+    HcStats st{};
+#ifdef AMREX_USE_GPU
+    const int rc = hc_integrate_struct_batch((int)t.size(), f[0].data(), f[1].data(), f[2].data(), f[3].data(), f[4].data(), f[5].data(),
+                                             t.data(), a, a_end, dt, sdc_iter, &p, &st, nullptr, nullptr);
+#else
+    const int rc = hc_integrate_struct_host((int)t.size(), f[0].data(), f[1].data(), f[2].data(), f[3].data(), f[4].data(), f[5].data(),
+                                            t.data(), a, a_end, dt, sdc_iter, &p, &st);
+#endif
+    finish(st, new_max);
+    return check(rc);
+}
+}  // namespace
+
+// HC/integrate_state_with_source_3d.cpp:50-185 (the hctest dump/replay hooks :82-125 stay with the reference's I/O layer)
+int Nyx::integrate_state_struct(MultiFab& S_old, MultiFab& S_new, MultiFab& D_old, MultiFab& hydro_src, MultiFab& IR, MultiFab& reset_src,
+                                const Real& a, const Real& a_end, const Real& delta_time, const int sdc_iter)
+{
+    const long int store_steps = new_max_sundials_steps;
+    std::vector<HcFab> f[6]; std::vector<HcBox> t;
+    for (MFIter mfi(S_old); mfi.isValid(); ++mfi) {
+        // C-ABI order == integrate_state_struct_mfin's: state, diag, state_n, hydro_src, reset_src, IR
+        f[0].push_back(to_fab(S_old.array(mfi))); f[1].push_back(to_fab(D_old.array(mfi))); f[2].push_back(to_fab(S_new.array(mfi)));
+        f[3].push_back(to_fab(hydro_src.array(mfi))); f[4].push_back(to_fab(reset_src.array(mfi))); f[5].push_back(to_fab(IR.array(mfi)));
+        t.push_back(to_box(mfi.validbox()));
+    }
+    return struct_batch(f, t, a, a_end, delta_time, sdc_iter, store_steps, new_max_sundials_steps);
+}
+
+// HC/integrate_state_with_source_3d.cpp:187-709: one tile
+int Nyx::integrate_state_struct_mfin(Array4<Real> const& state4, Array4<Real> const& diag_eos4, Array4<Real> const& state_n4,
+                                     Array4<Real> const& hydro_src4, Array4<Real> const& reset_src4, Array4<Real> const& IR4,
+                                     const Box& tbx, const Real& a, const Real& a_end, const Real& delta_time,
+                                     long int& old_max_steps, long int& new_max_steps, const int sdc_iter)
+{
+    std::vector<HcFab> f[6] = {{to_fab(state4)}, {to_fab(diag_eos4)}, {to_fab(state_n4)}, {to_fab(hydro_src4)}, {to_fab(reset_src4)}, {to_fab(IR4)}};
+    std::vector<HcBox> t{to_box(tbx)};
+    return struct_batch(f, t, a, a_end, delta_time, sdc_iter, old_max_steps, new_max_steps);
+}

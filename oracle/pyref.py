@@ -32,26 +32,30 @@ def _ptrs(arrs):
 class Reference:
     """The real reference (Nyx HeatCool + SUNDIALS CVODE) behind ref_driver.cpp."""
 
-    def __init__(self, variant="ser", treecool=TREECOOL, mean_rhob=None):
-        path = os.path.join(HERE, "_ref", f"libnyxhc_ref_{variant}.so")
+    def __init__(self, variant="ser", treecool=TREECOOL, mean_rhob=None, path=None):
+        # `path`: any library exporting the same nyxref_* driver entry points (tests/dropin_driver.cpp links them to the product)
+        path = path or os.path.join(HERE, "_ref", f"libnyxhc_ref_{variant}.so")
         if not os.path.exists(path):
             raise FileNotFoundError(path)
         self.lib = lib = C.CDLL(path)
         lib.nyxref_init.argtypes = [C.c_char_p, C.c_double]
-        lib.nyxref_rates.restype = _dp
-        lib.nyxref_rates.argtypes = [C.POINTER(C.c_long)]
+        if hasattr(lib, "nyxref_rates"):
+            lib.nyxref_rates.restype = _dp
+            lib.nyxref_rates.argtypes = [C.POINTER(C.c_long)]
         lib.nyxref_set.argtypes = [C.c_char_p, C.c_char_p]
         lib.nyxref_unset.argtypes = [C.c_char_p]
-        lib.nyxref_stats_get.argtypes = [C.POINTER(C.c_long)]
-        lib.nyxref_stats_count.restype = C.c_long
+        if hasattr(lib, "nyxref_stats_get"):
+            lib.nyxref_stats_get.argtypes = [C.POINTER(C.c_long)]
+            lib.nyxref_stats_count.restype = C.c_long
         lib.nyxref_get_max_steps.restype = C.c_long
         lib.nyxref_integrate_state_vec.argtypes = [C.c_int, C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int, _dpp, _dpp,
                                                    C.c_double, C.c_double, C.c_int]
         lib.nyxref_integrate_state_struct.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int] + [_dpp] * 6 + \
             [C.c_double, C.c_double, C.c_double, C.c_int]
-        lib.nyxref_ion_n.argtypes = [C.c_int, C.c_int] + [C.c_double] * 6 + [_dp]
-        lib.nyxref_eos_T_given_Re.argtypes = [C.c_int, C.c_int] + [C.c_double] * 5 + [_dp, _dp]
-        lib.nyxref_interp_to_this_z.argtypes = [C.c_double, _dp]
+        if hasattr(lib, "nyxref_ion_n"):
+            lib.nyxref_ion_n.argtypes = [C.c_int, C.c_int] + [C.c_double] * 6 + [_dp]
+            lib.nyxref_eos_T_given_Re.argtypes = [C.c_int, C.c_int] + [C.c_double] * 5 + [_dp, _dp]
+            lib.nyxref_interp_to_this_z.argtypes = [C.c_double, _dp]
         if mean_rhob is None:
             from nyx_b200 import synth
             mean_rhob = synth.mean_rhob()
@@ -73,7 +77,14 @@ class Reference:
         return np.ctypeslib.as_array(p, shape=(n.value,)).copy()
 
     def stats_reset(self):
-        self.lib.nyxref_stats_reset()
+        if hasattr(self.lib, "nyxref_stats_reset"):
+            self.lib.nyxref_stats_reset()
+
+    def last_stats(self):
+        """drop-in only: the HcStats counters of the last call"""
+        out = (C.c_longlong * 14)()
+        self.lib.nyxref_last_stats(out)
+        return list(out)
 
     def stats(self):
         """(n_instances, 8): nst, netf, nfe, nni, ncfn, nsetups, nfeLS, CVode flag — MFIter order."""

@@ -1,0 +1,116 @@
+"""The C++ host drop-in (nyx_b200/csrc/nyx_heatcool_dropin.cpp): same C++ symbols as the reference's translation units (CPU
+check), and -- on a GPU -- the same driver calls made against the reference build (oracle/_ref, its production default:
+tile-coupled CVODE) and against the drop-in, compared under the north-star contract (e, T within 10 x rtol; no failed cells)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from nyx_b200 import synth
+from tests import util
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+WANTED = ["Nyx::integrate_state_vec(", "Nyx::integrate_state_grownvec(", "Nyx::integrate_state_vec_mfin(", "Nyx::integrate_state_struct(",
+          "Nyx::integrate_state_struct_mfin("]
+
+
+def _defined_nyx_symbols(lib):
+    out = subprocess.run(["nm", "-D", "--defined-only", lib], capture_output=True, text=True, check=True).stdout
+    return sorted(ln.split()[-1] for ln in out.splitlines() if " T " in ln and "_ZN3Nyx" in ln)
+
+
+def test_dropin_defines_the_reference_symbols(built):
+    lib = built.build_dropin_check()
+    syms = _defined_nyx_symbols(lib)
+    dem = subprocess.run(["c++filt"], input="\n".join(syms), capture_output=True, text=True).stdout
+    for w in WANTED:
+        assert w in dem, f"{w} not defined by the drop-in"
+    ref = os.path.join(ROOT, "oracle", "_ref", "libnyxhc_ref_ser.so")
+    if os.path.exists(ref):
+        # identical mangled names == identical signatures (Source/Driver/Nyx.H:549-580)
+        assert set(syms) == set(_defined_nyx_symbols(ref))
+
+
+@pytest.fixture(scope="module")
+def dropin(built):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from oracle import pyref
+    return pyref.Reference(path=built.build_dropin_check())
+
+
+def _boxes_with_ghosts(n, ng_s, ng_d, z, seeds):
+    boxes, S, D = [], [], []
+    for b, seed in enumerate(seeds):
+        lo, hi = (b * n, 0, 0), ((b + 1) * n - 1, n - 1, n - 1)
+        m = n + 2 * ng_s
+        st, dg = synth.make_fab((m, m, m), seed=seed, z=z)
+        c = ng_s - ng_d
+        boxes.append(lo + hi)
+        S.append(st)
+        D.append(np.ascontiguousarray(dg[:, c:m - c, c:m - c, c:m - c]))
+    return boxes, S, D
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("grown", [False, True])
+def test_dropin_vec_vs_reference(dropin, reference, grown):
+    z, n, ng_s = 3.0, 16, 4
+    ng_d = 4 if grown else 1
+    a, dt = 1.0 / (1.0 + z), 0.5 * synth.step_dt(z)
+    boxes, S, D = _boxes_with_ghosts(n, ng_s, ng_d, z, (501, 502))
+    S_ref, D_ref = [x.copy() for x in S], [x.copy() for x in D]
+    S0 = [x.copy() for x in S]
+    assert reference.integrate_state_vec(boxes, S_ref, D_ref, a, dt, ng_state=ng_s, ng_diag=ng_d, grown=grown) == 0
+    assert dropin.integrate_state_vec(boxes, S, D, a, dt, ng_state=ng_s, ng_diag=ng_d, grown=grown) == 0
+    st = dropin.last_stats()
+    ncell = 2 * (n + (2 * ng_s if grown else 0)) ** 3
+    assert st[0] == ncell and st[1] == 0                      # n_cells, n_failed
+    for s, s_ref, s0, d, d_ref in zip(S, S_ref, S0, D, D_ref):
+        touched = s_ref[5] != s0[5]
+        assert touched.sum() == ncell // 2 and np.array_equal(s[5] != s0[5], touched)   # exactly the reference's cells were updated
+        assert np.abs(s[5][touched] / s_ref[5][touched] - 1).max() < 1e-3
+        assert np.abs(s[4][touched] / s_ref[4][touched] - 1).max() < 1e-3
+        for comp in (0, 1, 2, 3):
+            assert np.array_equal(s[comp], s0[comp])
+        cd = ng_s - ng_d
+        td = touched[cd:touched.shape[0] - cd, cd:touched.shape[1] - cd, cd:touched.shape[2] - cd] if cd else touched
+        assert np.abs(d[0][td] / d_ref[0][td] - 1).max() < 1e-3
+        assert np.abs(d[1][td] - d_ref[1][td]).max() < 1e-3
+
+
+@pytest.mark.gpu
+def test_dropin_struct_vs_reference(dropin, reference):
+    z, n = 3.0, 16
+    d = util.sdc_inputs(z, n, 511, 0.02)
+    r = {k: (v.copy() if hasattr(v, "copy") else v) for k, v in d.items()}
+    box = [(0, 0, 0, n - 1, n - 1, n - 1)]
+    order = ("s_old", "s_new", "diag", "hydro_src", "ir", "reset_src")      # the reference's argument order
+    assert reference.integrate_state_struct(box, *[[r[k]] for k in order], d["a"], d["a_end"], d["dt"], 0) == 0
+    assert dropin.integrate_state_struct(box, *[[d[k]] for k in order], d["a"], d["a_end"], d["dt"], 0) == 0
+    st = dropin.last_stats()
+    assert st[0] == n ** 3 and st[1] == 0
+    rel = np.abs(d["s_new"][5] / r["s_new"][5] - 1)
+    # the reference's own two modes differ by up to 1.06e-3 here; the bulk is far inside the contract
+    assert np.percentile(rel, 99.9) < 1e-3 and rel.max() < 5e-3
+    scale = np.abs(r["ir"][0]).max()
+    assert np.percentile(np.abs(d["ir"][0] - r["ir"][0]) / scale, 99.9) < 1e-3
+    assert np.array_equal(d["s_old"], r["s_old"])
+
+
+@pytest.mark.gpu
+def test_dropin_use_typical_steps_updates_max_steps(dropin):
+    z, n = 3.0, 12
+    a, dt = 1.0 / (1.0 + z), 0.5 * synth.step_dt(z)
+    boxes, S, D = _boxes_with_ghosts(n, 0, 0, z, (521,))
+    dropin.set("nyx.use_typical_steps", 1)
+    dropin.set("nyx.new_max_sundials_steps", 3)
+    try:
+        dropin.integrate_state_vec(boxes, S, D, a, dt)
+        st = dropin.last_stats()
+        assert dropin.lib.nyxref_get_max_steps(1) == max(3, st[4])        # new_max_sundials_steps = max over cells of nst
+    finally:
+        dropin.set("nyx.use_typical_steps", 0)
+        dropin.set("nyx.new_max_sundials_steps", 3)

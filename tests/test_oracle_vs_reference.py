@@ -59,11 +59,11 @@ def test_grownvec_ghost_cells_integrated(reference, port):
     state, diag = synth.make_fab((m, m, m), seed=311, z=z)
     lo, hi = (0, 0, 0), (n - 1, n - 1, n - 1)
     s1, d1 = state.copy(), diag.copy()
-    reference.set("nyx.sundials_tile_size", "1 1 1")
+    reference.set("fabarray.mfiter_tile_size", "1 1 1")      # grownvec tiles with the AMReX default tile size (:381), not sundials_tile_size
     try:
         reference.integrate_state_vec([lo + hi], [s1], [d1], a, dt, ng_state=ng, ng_diag=ng, grown=True)
     finally:
-        reference.set("nyx.sundials_tile_size", "1024000 8 8")
+        reference.set("fabarray.mfiter_tile_size", "1024000 8 8")
     glo, ghi = (-ng,) * 3, (n - 1 + ng,) * 3
     orig = state.copy()
     port.integrate_state_vec(state, diag, glo, ghi, a, dt, fab_lo=glo)
