@@ -346,8 +346,14 @@ def main():
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     hbm_ach = bytes_cell * stats.n_cells / t_kernel / 1e9
+    traffic = None
+    try:   # DRAM bytes per cell of the dominant kernel from the committed ncu capture, scaled to this launch's cell count
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            traffic = json.load(f)["dram_bytes_per_cell"] * stats.n_cells
+    except (OSError, KeyError, ValueError):
+        pass
     roofline = {"bound": "fp64", "achieved": achieved / 1e12, "peak": fp64_peak / 1e12, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
-                "traffic": None, "peak_source": "DFMA peak measured in this run by hc_measure_fp64_peak (MEASURED_PEAKS.json has no FP64 entry)",
+                "traffic": traffic, "traffic_note": "dram read+write bytes per launch: 41 B/cell from the 128^3 ncu capture in profiles/, scaled by cells (algorithmic: %d B/cell)" % (104 if struct else 56), "peak_source": "DFMA peak measured in this run by hc_measure_fp64_peak (MEASURED_PEAKS.json has no FP64 entry)",
                 "flops_per_cell": flops_local / stats.n_cells, "kernel": "hc_integrate_kernel<%s>" % ("PATH_STRUCT" if struct else "PATH_VEC"),
                 "hbm": {"achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak, "bytes_per_cell": bytes_cell,
                         "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback"}}
