@@ -1,2 +1,1 @@
-mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -q 2>&1 | grep -E "^E  |^tests/|passed|failed|^FAILED" | head -60
+timeout 120 python tools/gpu_diag_eos.py 2>&1 | tail -12

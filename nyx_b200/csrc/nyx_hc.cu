@@ -23,11 +23,20 @@
 
 // Build-time tuning knobs (measured on B200, profiles/): 384 lanes per SM leave 168 registers per lane (the integrator state
 // stays in registers), and the CTA-wide phase lock keeps one phase's code in the small instruction caches at a time.
+#ifndef HC_ARCH
+#define HC_ARCH 2                          // 1: register-resident lanes (hc_integrate_kernel); 2: phase-sorted lanes in shared memory (hc_sorted.cuh)
+#endif
 #ifndef HC_LOCKSTEP
 #define HC_LOCKSTEP 1                      // 0: warps free-run; 1: CTA-wide RHS / bookkeeping phase lock; 2: per-scheduler warp groups in lockstep
 #endif
 #ifndef HC_THREADS
 #define HC_THREADS 384                     // lanes (cells in flight) per SM; one persistent CTA per SM
+#endif
+#ifndef HC_SORTED_LANES_VEC
+#define HC_SORTED_LANES_VEC 384            // HC_ARCH 2: 496 B of shared memory per lane on the Strang path
+#endif
+#ifndef HC_SORTED_LANES_STRUCT
+#define HC_SORTED_LANES_STRUCT 320         // 616 B per lane on the SDC path
 #endif
 #if HC_LOCKSTEP == 2
 // SMSP-group lockstep: the warps that share a scheduler (warp id mod 4) -- and with it an L0 instruction cache -- step through
@@ -137,8 +146,9 @@ struct Totals {
 
 // gather one cell into a lane (HOT LOOP A of the reference: integrate_state_vec_3d.cpp:227-233,
 // ode_eos_initialize_arrays f_rhs_struct.H:180-209) and start its integration
-template <int PATH>
-__device__ __forceinline__ void load_cell(KLane<PATH>& ln, const KernelArgs& a, const TileDesc& t, int i, int j, int k) {
+template <class LaneT>
+__device__ __forceinline__ void load_cell(LaneT& ln, const KernelArgs& a, const TileDesc& t, int i, int j, int k) {
+    constexpr int PATH = LaneT::path;
     const Consts& c = a.k;
     const long long so = fab_off(t.f[F_STATE], i, j, k);
     ln.rho = t.f[F_STATE].p[so + DENS * t.f[F_STATE].nstride];
@@ -170,8 +180,9 @@ __device__ __forceinline__ void load_cell(KLane<PATH>& ln, const KernelArgs& a, 
 }
 
 // scatter a finished cell (HOT LOOP C: integrate_state_vec_3d.cpp:317-321, f_rhs_struct.H:290-291,438-444)
-template <int PATH>
-__device__ __forceinline__ void store_cell(const KLane<PATH>& ln, const KernelArgs& a, const TileDesc& t, int i, int j, int k, Totals& tot) {
+template <class LaneT>
+__device__ __forceinline__ void store_cell(const LaneT& ln, const KernelArgs& a, const TileDesc& t, int i, int j, int k, Totals& tot) {
+    constexpr int PATH = LaneT::path;
     const Consts& c = a.k;
     const long long dof = fab_off(t.f[F_DIAG], i, j, k);
     t.f[F_DIAG].p[dof + TEMP * t.f[F_DIAG].nstride] = ln.outT;
@@ -273,10 +284,10 @@ __global__ void __launch_bounds__(THREADS, 1) hc_integrate_kernel(const __grid_c
                 const int rank = __popc(m & lt_mask);
                 if (need && rank < avail) {
                     c_tile = w_tile; c_i = w_x + rank; c_j = w_j; c_k = w_k;
-                    load_cell<PATH>(ln, a, a.tiles[c_tile], c_i, c_j, c_k);
+                    load_cell(ln, a, a.tiles[c_tile], c_i, c_j, c_k);
                     // a cell whose integration cannot even start (illegal input) may be finished already: store it, stay free
                     if (ln.active()) need = false;
-                    else store_cell<PATH>(ln, a, a.tiles[c_tile], c_i, c_j, c_k, tot);
+                    else store_cell(ln, a, a.tiles[c_tile], c_i, c_j, c_k, tot);
                 }
                 w_x += min(avail, __popc(m));
                 m = __ballot_sync(0xffffffffu, need);
@@ -296,7 +307,7 @@ __global__ void __launch_bounds__(THREADS, 1) hc_integrate_kernel(const __grid_c
 #if HC_LOCKSTEP == 2
         f = ln.eval_request(tb, a.k);          // idle lanes evaluate a benign request: every lane takes part in the group barriers
         ln.resume(a.k, f, 0xffffffffu);        // (an idle lane falls through all stages)
-        if (act0 && !ln.active()) store_cell<PATH>(ln, a, a.tiles[c_tile], c_i, c_j, c_k, tot);
+        if (act0 && !ln.active()) store_cell(ln, a, a.tiles[c_tile], c_i, c_j, c_k, tot);
 #else
         if (act0) f = ln.eval_request(tb, a.k);
 #if HC_LOCKSTEP
@@ -308,7 +319,7 @@ __global__ void __launch_bounds__(THREADS, 1) hc_integrate_kernel(const __grid_c
         const unsigned rmask = __ballot_sync(0xffffffffu, act0);
         if (act0) {
             ln.resume(a.k, f, rmask);
-            if (!ln.active()) store_cell<PATH>(ln, a, a.tiles[c_tile], c_i, c_j, c_k, tot);
+            if (!ln.active()) store_cell(ln, a, a.tiles[c_tile], c_i, c_j, c_k, tot);
         }
 #endif
         __syncwarp();
@@ -353,6 +364,8 @@ __global__ void __launch_bounds__(THREADS, 1) hc_eos_kernel(const __grid_constan
     __syncthreads();
     if (threadIdx.x < S_COUNT) atomicAdd(&a.dstats[threadIdx.x], s_stats[threadIdx.x]);
 }
+
+#include "hc_sorted.cuh"
 
 // FP64 FMA throughput probe: 8 independent chains per thread, explicit __fma_rn (unaffected by -fmad=false)
 __global__ void __launch_bounds__(256) hc_dfma_peak_kernel(double* out, int iters, double seed) {
@@ -470,6 +483,18 @@ int launch(int path, int ntiles, const HcFab* const* fabs, int nf, const HcBox* 
 
     const long long want = (ncells + THREADS - 1) / THREADS;
     const int grid = (int)std::min<long long>(want, dt.sm_count);
+#if HC_ARCH == 2
+    constexpr int LV = HC_SORTED_LANES_VEC, LS = HC_SORTED_LANES_STRUCT;
+    if (path == PATH_VEC) {
+        const int g = (int)std::min<long long>((ncells + LV - 1) / LV, dt.sm_count);
+        if (int rc = set_smem_attr(sorted::hc_sorted_kernel<PATH_VEC, LV>, dt, 0, sorted::Layout<PATH_VEC, LV>::total)) return rc;
+        sorted::hc_sorted_kernel<PATH_VEC, LV><<<g, LV, sorted::Layout<PATH_VEC, LV>::total, stream>>>(a);
+    } else if (path == PATH_STRUCT) {
+        const int g = (int)std::min<long long>((ncells + LS - 1) / LS, dt.sm_count);
+        if (int rc = set_smem_attr(sorted::hc_sorted_kernel<PATH_STRUCT, LS>, dt, 1, sorted::Layout<PATH_STRUCT, LS>::total)) return rc;
+        sorted::hc_sorted_kernel<PATH_STRUCT, LS><<<g, LS, sorted::Layout<PATH_STRUCT, LS>::total, stream>>>(a);
+    } else {
+#else
     if (path == PATH_VEC) {
         if (int rc = set_smem_attr(hc_integrate_kernel<PATH_VEC>, dt, 0, SMEM_INTEGRATE)) return rc;
         hc_integrate_kernel<PATH_VEC><<<grid, THREADS, SMEM_INTEGRATE, stream>>>(a);
@@ -477,6 +502,7 @@ int launch(int path, int ntiles, const HcFab* const* fabs, int nf, const HcBox* 
         if (int rc = set_smem_attr(hc_integrate_kernel<PATH_STRUCT>, dt, 1, SMEM_INTEGRATE)) return rc;
         hc_integrate_kernel<PATH_STRUCT><<<grid, THREADS, SMEM_INTEGRATE, stream>>>(a);
     } else {
+#endif
         if (int rc = set_smem_attr(hc_eos_kernel, dt, 2, SMEM_EOS)) return rc;
         hc_eos_kernel<<<grid, THREADS, SMEM_EOS, stream>>>(a);
     }
