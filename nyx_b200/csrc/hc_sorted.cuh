@@ -43,7 +43,7 @@ struct Layout {
     static constexpr size_t bytes_order = (size_t)LANES * sizeof(unsigned short);
     static constexpr size_t bytes_cnt = (size_t)NKEY * WARPS * sizeof(int) * 2;
     static constexpr size_t total = bytes_d + bytes_i + bytes_order + bytes_cnt;
-    static_assert(total <= 227 * 1024, "shared memory budget of one sm_100 CTA");
+    static_assert((total + 2048) * HC_SORTED_CTAS <= 228 * 1024, "shared memory budget of one sm_100 SM");
 };
 
 template <int STRIDE>
@@ -83,7 +83,7 @@ __device__ __forceinline__ void unpack_ints(LaneT& ln, unsigned w0, unsigned w1)
 }
 
 template <int PATH, int LANES>
-__global__ void __launch_bounds__(LANES, 1) hc_sorted_kernel(const __grid_constant__ KernelArgs a) {
+__global__ void __launch_bounds__(LANES, HC_SORTED_CTAS) hc_sorted_kernel(const __grid_constant__ KernelArgs a) {
     using L = Layout<PATH, LANES>;
     using LaneT = Lane<PATH, ArrSmemT<LANES>>;
     __shared__ unsigned long long s_stats[S_COUNT];

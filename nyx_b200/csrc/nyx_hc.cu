@@ -35,6 +35,9 @@
 #ifndef HC_SORTED_LANES_VEC
 #define HC_SORTED_LANES_VEC 384            // HC_ARCH 2: 496 B of shared memory per lane on the Strang path
 #endif
+#ifndef HC_SORTED_CTAS
+#define HC_SORTED_CTAS 1                   // HC_ARCH 2: CTAs per SM (each with its own phase barriers; LANES x CTAS lanes in flight per SM)
+#endif
 #ifndef HC_SORTED_LANES_STRUCT
 #define HC_SORTED_LANES_STRUCT 320         // 616 B per lane on the SDC path
 #endif
@@ -486,11 +489,11 @@ int launch(int path, int ntiles, const HcFab* const* fabs, int nf, const HcBox* 
 #if HC_ARCH == 2
     constexpr int LV = HC_SORTED_LANES_VEC, LS = HC_SORTED_LANES_STRUCT;
     if (path == PATH_VEC) {
-        const int g = (int)std::min<long long>((ncells + LV - 1) / LV, dt.sm_count);
+        const int g = (int)std::min<long long>((ncells + LV - 1) / LV, (long long)dt.sm_count * HC_SORTED_CTAS);
         if (int rc = set_smem_attr(sorted::hc_sorted_kernel<PATH_VEC, LV>, dt, 0, sorted::Layout<PATH_VEC, LV>::total)) return rc;
         sorted::hc_sorted_kernel<PATH_VEC, LV><<<g, LV, sorted::Layout<PATH_VEC, LV>::total, stream>>>(a);
     } else if (path == PATH_STRUCT) {
-        const int g = (int)std::min<long long>((ncells + LS - 1) / LS, dt.sm_count);
+        const int g = (int)std::min<long long>((ncells + LS - 1) / LS, (long long)dt.sm_count * HC_SORTED_CTAS);
         if (int rc = set_smem_attr(sorted::hc_sorted_kernel<PATH_STRUCT, LS>, dt, 1, sorted::Layout<PATH_STRUCT, LS>::total)) return rc;
         sorted::hc_sorted_kernel<PATH_STRUCT, LS><<<g, LS, sorted::Layout<PATH_STRUCT, LS>::total, stream>>>(a);
     } else {

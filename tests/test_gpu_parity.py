@@ -125,14 +125,18 @@ def test_struct_matches_oracle(hc_lib, port, z, seed, src, flash):
     same = _compare_counts(cs, pst, f"struct z={z} {flash}", chaotic_cells=chaotic).reshape(n, n, n)
     ok3 = ((pst[:, 7] == 0) & (cs["flag"] == 0)).reshape(n, n, n)   # cells that fail are compared on flags/counters only
     e_rel = _rel(out["s_new"][5], ref["s_new"][5])
-    ir_abs = np.abs(out["ir"][0] - ref["ir"][0]) / np.abs(ref["ir"][0]).max()
+    # I_R carries the same information as the energy update, rho_out * de * a_end^2 / (dt * a_half) (f_rhs_struct.H:307): its difference is
+    # converted back to an energy difference and weighed with the integrator's own error weight, like werr
+    ahalf = 0.5 * (d["a"] + d["a_end"])
+    de_ir = np.abs(out["ir"][0] - ref["ir"][0]) * d["dt"] * ahalf / (d["a_end"] ** 2) / ref["s_new"][0]
+    ir_w = de_ir / (1e-4 * np.abs(ref["s_new"][5] / ref["s_new"][0]) + 1e-4 * np.abs(d["s_old"][5] / d["s_old"][0]))
     # all cells, whatever step sequence they took: 10 x the integrator's tolerance (relative OR absolute part, as CVODE weighs them)
     werr = _weighted_err(out["s_new"][5], ref["s_new"][5], ref["s_new"][0], d["s_old"][5], d["s_old"][0])
     assert werr[ok3].max() < 10.0, werr[ok3].max()
     assert np.mean(e_rel[ok3] > E_T_TOL) < 1e-3          # and the plain relative 10 x rtol bound in all but isolated strongly-cooled cells
     m = same & ok3
     # same step sequence: 1/10 of the tolerance itself (<= 1e-5 relative for cells that keep their energy scale)
-    assert werr[m].max() < 0.1 and ir_abs[m].max() < 1e-7, (werr[m].max(), e_rel[m].max(), ir_abs[m].max())
+    assert werr[m].max() < 0.1 and ir_w[m].max() < 0.1, (werr[m].max(), e_rel[m].max(), ir_w[m].max())
     # diag holds T, ne of the LAST RHS evaluation (f_rhs_struct.H:290-291), not T(e_out).  That evaluation is often the
     # finite-difference probe of the diagonal Jacobian at y + 0.1*rl1*(h*f - zn[1]) (cvode_diag.c:364), whose offset is a
     # cancellation residue: a last-bit difference in f moves it by O(1), so this diagnostic T differs by up to ~1e-4
