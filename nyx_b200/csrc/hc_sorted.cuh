@@ -82,6 +82,17 @@ __device__ __forceinline__ void unpack_ints(LaneT& ln, unsigned w0, unsigned w1)
     ln.jcur = (w1 >> 10) & 1u; ln.nls_jcur = (w1 >> 11) & 1u; ln.floor_hit = (int)((w1 >> 12) & 1u);
 }
 
+#if defined(HC_PHASE_TIMING)
+// diagnostics build only: per-phase clock64 totals summed over warps: [0] rounds*warps [1] sort [2] B work [3] B barrier wait [4] R work [5] R barrier wait
+// [6] active lanes at R (sum over rounds) [7] kernel cycles*warps [8..15] lanes per sort key (sum over rounds)
+// B work split: [16] load lane [17] resume + store_cell [18] refill [19] write back; [24..31] B work cycles of the warps whose first lane has
+// sort key 0..7, [32..39] number of such warp-rounds, [40..47] their active lanes in resume()
+__device__ unsigned long long g_phase[48];
+#define HC_TICK(slot) do { const long long t_ = clock64(); ph[slot] += (unsigned long long)(t_ - t_last); t_last = t_; } while (0)
+#else
+#define HC_TICK(slot) do { } while (0)
+#endif
+
 template <int PATH, int LANES>
 __global__ void __launch_bounds__(LANES, HC_SORTED_CTAS) hc_sorted_kernel(const __grid_constant__ KernelArgs a) {
     using L = Layout<PATH, LANES>;
@@ -115,6 +126,13 @@ __global__ void __launch_bounds__(LANES, HC_SORTED_CTAS) hc_sorted_kernel(const 
     int w_tile = 0, w_j = 0, w_k = 0, w_x = 0, w_xend = 0;   // the warp's current chunk (warp-uniform)
     bool queue_empty = false;
     __syncthreads();
+#if defined(HC_PHASE_TIMING)
+    unsigned long long ph[48];
+#pragma unroll
+    for (int i = 0; i < 48; ++i) ph[i] = 0ull;
+    long long t_last = clock64();
+    const long long t_begin = t_last;
+#endif
 
     for (;;) {
         // ================= phase S: stable counting sort of the lanes by integrator phase
@@ -141,6 +159,14 @@ __global__ void __launch_bounds__(LANES, HC_SORTED_CTAS) hc_sorted_kernel(const 
             __syncthreads();
             s_order[s_base[key * L::WARPS + warp] + rank] = (unsigned short)tid;
             __syncthreads();
+#if defined(HC_PHASE_TIMING)
+            if (rank == 0) {
+#pragma unroll
+                for (int kk = 0; kk < NKEY; ++kk) if (key == kk) ph[8 + kk] += __popc(same);
+            }
+            ph[0] += 1;
+#endif
+            HC_TICK(1);
         }
 
         // ================= phase B: bookkeeping of lane order[tid]
@@ -171,13 +197,23 @@ __global__ void __launch_bounds__(LANES, HC_SORTED_CTAS) hc_sorted_kernel(const 
             int c_tile = si[SI_TILE * LANES + my], c_i = si[SI_CI * LANES + my], c_j = si[SI_CJ * LANES + my], c_k = si[SI_CK * LANES + my];
             const double f = sd[SD_FVAL * LANES + my];
 
+            HC_TICK(16);
+#if defined(HC_PHASE_TIMING)
+            const long long t_b0 = clock64();
+            const int key0 = __shfl_sync(0xffffffffu, sort_key<LaneT>(w0, w1), 0);
+#endif
             const bool act0 = ln.active();
             const unsigned rmask = __ballot_sync(0xffffffffu, act0);
+#if defined(HC_PHASE_TIMING)
+            ln.dbg_on = (key0 == K_LSETUP) && (__shfl_sync(0xffffffffu, sort_key<LaneT>(w0, w1), 31) == K_LSETUP);   // warps made of Jacobian-setup lanes only
+            ln.dbg_last = clock64();
+#endif
             if (act0) {
                 ln.resume(c, f, rmask);
                 if (!ln.active()) store_cell(ln, a, a.tiles[c_tile], c_i, c_j, c_k, tot);
             }
             __syncwarp();
+            HC_TICK(17);
             // ---- refill: idle lanes take the next cells of the warp's chunk (new chunks from the global queue)
             if (!queue_empty) {
                 bool need = !ln.active();
@@ -210,6 +246,7 @@ __global__ void __launch_bounds__(LANES, HC_SORTED_CTAS) hc_sorted_kernel(const 
                     m = __ballot_sync(0xffffffffu, need);
                 }
             }
+            HC_TICK(18);
             // ---- write the lane back
             pack_ints(ln, w0, w1);
             si[SI_W0 * LANES + my] = (int)w0; si[SI_W1 * LANES + my] = (int)w1;
@@ -226,8 +263,19 @@ __global__ void __launch_bounds__(LANES, HC_SORTED_CTAS) hc_sorted_kernel(const 
             }
             si[SI_TILE * LANES + my] = c_tile; si[SI_CI * LANES + my] = c_i; si[SI_CJ * LANES + my] = c_j; si[SI_CK * LANES + my] = c_k;
             active_after = ln.active();
+#if defined(HC_PHASE_TIMING)
+            {
+                const long long t_b1 = clock64();
+                const int nact = __popc(rmask);
+#pragma unroll
+                for (int kk = 0; kk < NKEY; ++kk) if (key0 == kk) { ph[24 + kk] += (unsigned long long)(t_b1 - t_b0); ph[32 + kk] += 1; ph[40 + kk] += nact; }
+            }
+#endif
         }
-        if (!__syncthreads_or(active_after)) break;   // nothing in flight and the queue is empty (also publishes the lanes for phase R)
+        HC_TICK(19);
+        const bool any_active = __syncthreads_or(active_after);
+        HC_TICK(3);
+        if (!any_active) break;   // nothing in flight and the queue is empty (also publishes the lanes for phase R)
 
         // ================= phase R: thread t evaluates the request of lane t
         {
@@ -260,9 +308,23 @@ __global__ void __launch_bounds__(LANES, HC_SORTED_CTAS) hc_sorted_kernel(const 
                 si[(SI_CNT0 + 8) * LANES + tid] += ln.ne_iters;
                 si[(SI_CNT0 + 10) * LANES + tid] += ln.n_eos;
             }
+#if defined(HC_PHASE_TIMING)
+            ph[6] += ln.active() ? 1 : 0;
+#endif
         }
+        HC_TICK(4);
         __syncthreads();
+        HC_TICK(5);
     }
+#if defined(HC_PHASE_TIMING)
+    ph[7] = (unsigned long long)(clock64() - t_begin);
+#pragma unroll
+    for (int i = 0; i < 48; ++i) {
+        unsigned long long v = ph[i];
+        if (i == 6 || (i >= 8 && i < 16)) { for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o); }   // per-thread quantities
+        if (lane_id == 0) atomicAdd(&g_phase[i], v);
+    }
+#endif
 
     flush_totals(tot, s_stats, a.dstats);
 }

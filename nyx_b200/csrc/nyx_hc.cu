@@ -63,6 +63,16 @@ __host__ __device__ __forceinline__ bool hc_group_all(bool pred) {
 #define HC_GROUP_ALL(pred) hc_group_all(pred)
 #define HC_GROUP_RHS 1
 #endif
+#if defined(HC_PHASE_TIMING)
+// diagnostics build: cycles between the stage boundaries of Lane::resume(), summed over the warps the kernel switches on
+__device__ unsigned long long g_stage[16];
+__host__ __device__ __forceinline__ void hc_stage_tick(long long& last, bool on, int slot) {
+#if defined(__CUDA_ARCH__)
+    if (on) { const long long t_ = clock64(); if ((threadIdx.x & 31u) == 0u) atomicAdd(&g_stage[slot], (unsigned long long)(t_ - last)); last = t_; }
+#endif
+}
+#define HC_STAGE_TICK(ln, slot) hc_stage_tick((ln).dbg_last, (ln).dbg_on, slot)
+#endif
 #include "hc_host.hpp"
 
 namespace {
@@ -705,6 +715,24 @@ int hc_measure_fp64_peak(double* flops_per_s) {
     *flops_per_s = best;
     return HC_OK;
 }
+
+#if defined(HC_PHASE_TIMING)
+// diagnostics build only (tools/build_variants.sh): read and reset the per-phase cycle totals of the sorted kernel
+int hc_debug_phase(unsigned long long* out48) {
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpyFromSymbol(out48, sorted::g_phase, 48 * sizeof(unsigned long long)));
+    unsigned long long zero[48] = {0};
+    CUDA_TRY(cudaMemcpyToSymbol(sorted::g_phase, zero, sizeof zero));
+    return HC_OK;
+}
+int hc_debug_stage(unsigned long long* out16) {
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpyFromSymbol(out16, g_stage, 16 * sizeof(unsigned long long)));
+    unsigned long long zero[16] = {0};
+    CUDA_TRY(cudaMemcpyToSymbol(g_stage, zero, sizeof zero));
+    return HC_OK;
+}
+#endif
 
 int hc_sync(void* stream) {
     CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));

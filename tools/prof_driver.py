@@ -31,3 +31,32 @@ for r in range(reps):
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     print(f"{path} n={n} z={z} rep {r}: {ms:.3f} ms  {n**3 / ms * 1e3:.4e} cell-updates/s  failed {st.n_failed} sum_nst {st.sum_nst}", flush=True)
+if hasattr(hc.lib, "hc_debug_phase"):
+    import ctypes
+    buf = (ctypes.c_ulonglong * 48)()
+    hc.lib.hc_debug_phase(buf)
+    v = [int(x) for x in buf]
+    rw = max(v[0], 1)
+    tot = max(v[7], 1)
+    print(f"phase timing (sum over {reps} reps): warp-rounds {v[0]}  cycles per warp-round {v[7] / rw:.0f}")
+    names = {1: "sort", 16: "B load", 17: "B resume+store", 18: "B refill", 19: "B writeback", 3: "B barrier wait", 4: "R work", 5: "R barrier wait"}
+    for k, nm in names.items():
+        print(f"  {nm:18s} {100.0 * v[k] / tot:6.2f} %   {v[k] / rw:9.0f} cycles per warp-round")
+    print(f"  active lanes at R per warp-round: {v[6] / rw:.2f} / 32")
+    keys = ["NEWTON", "SETUP_REQ", "LSETUP", "HIN", "INIT", "ETEST", "FINAL", "IDLE"]
+    print("  lanes per key per warp-round: " + ", ".join(f"{k}={v[8 + i] / rw:.2f}" for i, k in enumerate(keys)))
+    print("  B work of a warp by the sort key of its first lane (cycles per such warp-round, share of warp-rounds, active lanes in resume):")
+    for i, k in enumerate(keys):
+        if v[32 + i]:
+            print(f"    {k:10s} {v[24 + i] / v[32 + i]:9.0f} cycles   {100.0 * v[32 + i] / rw:5.1f} % of warp-rounds   {v[40 + i] / v[32 + i]:5.1f} lanes")
+if hasattr(hc.lib, "hc_debug_stage"):
+    import ctypes
+    buf = (ctypes.c_ulonglong * 16)()
+    hc.lib.hc_debug_stage(buf)
+    v = [int(x) for x in buf]
+    tot = max(sum(v), 1)
+    nm = ["stage 0 (handlers)", "HIN request", "Newton iteration", "Newton error", "NLS success + error test", "complete_step", "prepare_next_step",
+          "cvStep tail rest", "after-hin", "STEP_TOP", "handle nflag", "predict", "set_coeffs", "attempt rest", "Newton top", "done/finalize"]
+    print("resume() of the all-LSETUP warps, share of cycles per stage:")
+    for i in range(16):
+        print(f"    {nm[i]:26s} {100.0 * v[i] / tot:6.2f} %")
