@@ -145,6 +145,10 @@ int hc_integrate_struct_host(int ntiles, const HcFab* s_old, const HcFab* diag, 
 /* measured FP64 FMA throughput of the current device in FLOP/s (2 flops per DFMA), for roofline denominators */
 int hc_measure_fp64_peak(double* flops_per_s);
 
+/* self-test of the kernels' table-driven log10 (hc_device.cuh: fast_log10): y[i] = log10(x[i]) for n HOST doubles, evaluated on the device
+ * by the same inline function the RHS fast path uses; bad[i] != 0 where the fast path would hand over to the library log10 */
+int hc_selftest_log10(const double* x, double* y, int* bad, long long n);
+
 /* blocks until work queued on `stream` is done (cudaStreamSynchronize) */
 int hc_sync(void* stream);
 

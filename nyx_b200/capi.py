@@ -101,6 +101,7 @@ def declare(lib, prefix="hc_"):
     lib.hc_integrate_vec_host.argtypes = [C.c_int, fp, fp, bp, C.c_double, C.c_double, pp, sp]
     lib.hc_integrate_struct_host.argtypes = [C.c_int] + [fp] * 6 + [bp, C.c_double, C.c_double, C.c_double, C.c_int, pp, sp]
     lib.hc_measure_fp64_peak.argtypes = [_dp]
+    lib.hc_selftest_log10.argtypes = [_dp, _dp, C.POINTER(C.c_int), C.c_longlong]
     lib.hc_sync.argtypes = [C.c_void_p]
     return lib
 
@@ -192,6 +193,14 @@ class NyxHC:
         v = C.c_double()
         self.check(self.lib.hc_measure_fp64_peak(C.byref(v)))
         return v.value
+
+    def selftest_log10(self, x):
+        """log10 of a float64 array through the kernels' table-driven fast path -> (y, bad)"""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.empty_like(x)
+        bad = np.empty(x.size, dtype=np.int32)
+        self.check(self.lib.hc_selftest_log10(x.ctypes.data_as(_dp), y.ctypes.data_as(_dp), bad.ctypes.data_as(C.POINTER(C.c_int)), x.size))
+        return y, bad
 
     def sync(self, stream=None):
         self.check(self.lib.hc_sync(stream))

@@ -116,6 +116,20 @@ inline void interleave_tables(const double* R, std::vector<double>& ionx, std::v
     }
 }
 
+// the table of fast_log10 (hc_device.cuh): entry i = {r_i, Lhi_i, Llo_i, 0}, r_i = double(1/c_i), c_i = 1 + (i + 1/2)/128,
+// Lhi_i + Llo_i = -log10(r_i) evaluated in 80-bit extended precision, Lhi_i truncated to a multiple of 2^-42
+inline void build_log10_table(std::vector<double>& out) {
+    out.assign((size_t)LOG_TAB_N * 4, 0.0);
+    for (int i = 0; i < LOG_TAB_N; ++i) {
+        const double r = (double)(1.0L / (1.0L + ((long double)i + 0.5L) / (long double)LOG_TAB_N));
+        const long double L = -log10l((long double)r);
+        const double Lhi = (double)(floorl(L * 4398046511104.0L) / 4398046511104.0L);   // 2^42
+        out[4 * (size_t)i + 0] = r;
+        out[4 * (size_t)i + 1] = Lhi;
+        out[4 * (size_t)i + 2] = (double)(L - (long double)Lhi);
+    }
+}
+
 inline void default_params(HcParams* p) {
     std::memset(p, 0, sizeof *p);
     p->rtol = 1e-4; p->atol_factor = 1e-4; p->h_species = 0.76; p->gamma_minus_1 = 5.0 / 3.0 - 1.0;

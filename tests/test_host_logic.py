@@ -117,6 +117,59 @@ def _declared_symbols():
     return sorted(set(re.findall(r"\b(hc_[A-Za-z0-9_]+)\s*\(", txt)))
 
 
+def test_log10_table_and_algorithm(harness):
+    """The table hc_tables_upload builds for the device's fast_log10, and the algorithm itself emulated in exact rational
+    arithmetic (every FMA = exact product-sum, one rounding): max error well below 1 ulp against a 50-digit log10."""
+    import math
+    import struct
+    from decimal import Decimal, getcontext
+    from fractions import Fraction as F
+    getcontext().prec = 50
+    tab = np.zeros(128 * 4)
+    harness.lib.hh_log10_table.argtypes = [C.POINTER(C.c_double)]
+    harness.lib.hh_log10_table.restype = None
+    harness.lib.hh_log10_table(tab.ctypes.data_as(C.POINTER(C.c_double)))
+    tab = tab.reshape(128, 4)
+
+    def dlog10(fr):
+        return Decimal(fr.numerator).log10() - Decimal(fr.denominator).log10()
+
+    for i in range(128):
+        r, lhi, llo, pad = (float(v) for v in tab[i])
+        assert r == float(1 / F(2 * 128 + 2 * i + 1, 2 * 128)) and pad == 0.0
+        assert (lhi * 2.0 ** 42).is_integer() and 0.0 <= lhi < 0.31
+        assert abs(Decimal(lhi) + Decimal(llo) + dlog10(F(r))) < Decimal(2) ** -62
+    log2 = Decimal(2).log10()
+    log2_hi, log2_lo = float.fromhex("0x1.34413509f7000p-2"), float.fromhex("0x1.3fde623e2566bp-43")
+    assert (log2_hi * 2.0 ** 42).is_integer() and abs(Decimal(log2_hi) + Decimal(log2_lo) - log2) < Decimal(2) ** -95
+    coef = [float.fromhex(h) for h in ("0x1.bcb7b1526e50ep-2", "-0x1.bcb7b1526e50ep-3", "0x1.287a7636f435fp-3", "-0x1.bcb7b1526e50ep-4",
+                                      "0x1.63c62775250d8p-4", "-0x1.287a7636f435fp-4")]
+
+    def fma(a, b, c):
+        return float(F(a) * F(b) + F(c))
+
+    def flog10(x):
+        bits = struct.unpack("<q", struct.pack("<d", x))[0]
+        e = ((bits >> 52) & 0x7ff) - 1023
+        m = struct.unpack("<d", struct.pack("<q", (bits & ((1 << 52) - 1)) | (1023 << 52)))[0]
+        r, lhi, llo, _ = (float(v) for v in tab[(bits >> 45) & 127])
+        z = fma(m, r, -1.0)
+        q = coef[5]
+        for c in coef[4::-1]:
+            q = fma(z, q, c)
+        small = fma(z, q, fma(float(e), log2_lo, llo))
+        big = fma(float(e), log2_hi, lhi)
+        assert F(big) == F(float(e)) * F(log2_hi) + F(lhi)        # exact by construction
+        return float(F(big) + F(small))
+
+    rng = np.random.default_rng(5)
+    worst = 0.0
+    for x in 10.0 ** rng.uniform(0.35, 10.0, 3000):
+        y, ref = flog10(float(x)), dlog10(F(float(x)))
+        worst = max(worst, float(abs(Decimal(y) - ref) / Decimal(math.ulp(float(ref)))))
+    assert worst < 0.52, worst
+
+
 def test_cabi_exports_every_declared_symbol(built):
     lib = C.CDLL(built.build_cuda())
     names = _declared_symbols()
