@@ -332,7 +332,7 @@ def main():
     ncell_global = gstats["n_cells"]
     value = ncell_global * args.steps / t_max
 
-    # ---- roofline of the dominant kernel (hc_integrate_kernel): algorithmic flops / event time vs measured DFMA peak
+    # ---- roofline of the dominant kernel (sorted::hc_sorted_kernel): algorithmic flops / event time vs measured DFMA peak
     fp64_peak = hc.measure_fp64_peak()
     flops_local = sharded.algorithmic_flops(stats)
     t_kernel = t_local / args.steps
@@ -353,8 +353,8 @@ def main():
     except (OSError, KeyError, ValueError):
         pass
     roofline = {"bound": "fp64", "achieved": achieved / 1e12, "peak": fp64_peak / 1e12, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
-                "traffic": traffic, "traffic_note": "dram read+write bytes per launch: 41 B/cell from the 128^3 ncu capture in profiles/, scaled by cells (algorithmic: %d B/cell)" % (104 if struct else 56), "peak_source": "DFMA peak measured in this run by hc_measure_fp64_peak (MEASURED_PEAKS.json has no FP64 entry)",
-                "flops_per_cell": flops_local / stats.n_cells, "kernel": "hc_integrate_kernel<%s>" % ("PATH_STRUCT" if struct else "PATH_VEC"),
+                "traffic": traffic, "traffic_note": "dram read+write bytes per launch: B/cell of the ncu --set full capture in profiles/r1_traffic.json, scaled by cells (algorithmic: %d B/cell)" % (104 if struct else 56), "peak_source": "DFMA peak measured in this run by hc_measure_fp64_peak (MEASURED_PEAKS.json has no FP64 entry)",
+                "flops_per_cell": flops_local / stats.n_cells, "kernel": "sorted::hc_sorted_kernel<%s>" % ("PATH_STRUCT, 320" if struct else "PATH_VEC, 384"),
                 "hbm": {"achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak, "bytes_per_cell": bytes_cell,
                         "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback"}}
 
@@ -382,7 +382,7 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             t_e2e = float(tt.item())
         e2e = {"value": ncell_global * n_e2e / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": n_e2e,
-               "ms_per_step": 1e3 * t_e2e / n_e2e, "api": "hc_integrate_%s_host on pinned host FABs" % args.path, "n_failed": st_h.n_failed}
+               "ms_per_step": 1e3 * t_e2e / n_e2e, "api": "hc_integrate_%s_host on pinned host FABs (H2D / kernel / D2H pipelined over 8 groups of boxes)" % args.path, "n_failed": st_h.n_failed}
 
     # ---- CPU baseline (rank 0, N = 1 only): the reference's OpenMP implementation on a bounded sample of the same boxes
     cpu = None

@@ -467,8 +467,9 @@ int set_smem_attr(KernelT kernel, DeviceTables& dt, int slot, size_t bytes) {
 }
 
 // Common launcher: build tile descriptors, stream-ordered scratch, launch, optionally read the statistics back.
+// `ext_dstats` (device, 14 x u64, zeroed by the caller): accumulate the statistics there instead (several launches of one call).
 int launch(int path, int ntiles, const HcFab* const* fabs, int nf, const HcBox* tiles, const Consts& k, HcStats* stats,
-           HcCellStat* cell_stats, cudaStream_t stream) {
+           HcCellStat* cell_stats, cudaStream_t stream, unsigned long long* ext_dstats = nullptr) {
     int dev; if (int rc = current_device(dev)) return rc;
     DeviceTables& dt = g_dev[dev];
     if (!dt.ionx) { set_err("hc_tables_upload has not been called on device %d", dev); return HC_ERR_NO_TABLES; }
@@ -500,7 +501,7 @@ int launch(int path, int ntiles, const HcFab* const* fabs, int nf, const HcBox* 
     a.ncells = ncells;
     a.nchunks = nchunks;
     a.queue = reinterpret_cast<unsigned long long*>(scratch);
-    a.dstats = reinterpret_cast<unsigned long long*>(scratch + 64);
+    a.dstats = ext_dstats ? ext_dstats : reinterpret_cast<unsigned long long*>(scratch + 64);
     a.cell_stats = cell_stats;
     a.ionx = dt.ionx; a.iony = dt.iony; a.cool = dt.cool; a.logtab = dt.logtab;
 
@@ -530,7 +531,7 @@ int launch(int path, int ntiles, const HcFab* const* fabs, int nf, const HcBox* 
         hc_eos_kernel<<<grid, THREADS, SMEM_EOS, stream>>>(a);
     }
     CUDA_TRY(cudaGetLastError());
-    if (stats) {
+    if (stats && !ext_dstats) {
         // the pageable `stats` target makes this copy synchronous with respect to the host
         CUDA_TRY(cudaMemcpyAsync(stats, scratch + 64, sizeof(HcStats), cudaMemcpyDeviceToHost, stream));
         CUDA_TRY(cudaStreamSynchronize(stream));
@@ -539,42 +540,109 @@ int launch(int path, int ntiles, const HcFab* const* fabs, int nf, const HcBox* 
     return HC_OK;
 }
 
-// ---- host-buffer staging -----------------------------------------------------------------------------------
-struct Staged {
-    std::vector<HcFab> dev;       // device-side fabs (same geometry)
-    std::vector<double*> bufs;
+// ---- host-buffer entry points: staged and pipelined --------------------------------------------------------------------
+// The tiles are cut into groups; group g+1 is copied to the device (stream h2d) while group g is integrated (stream comp) and
+// group g-1 is copied back (stream d2h): except for the first H2D and the last D2H the transfers hide behind the kernel.
+// Device buffers come from the stream-ordered pool (its release threshold is raised once, so that repeated calls do not
+// re-acquire memory from the driver).
+struct HostSlot {
+    const HcFab* host;          // ntiles host FABs
+    std::vector<int> in, out;   // components copied to the device before / back to the host after the kernel
 };
+struct HostPipe {
+    cudaStream_t h2d = nullptr, comp = nullptr, d2h = nullptr;
+    bool ready = false;
+};
+HostPipe g_pipe[64];
+constexpr int HOST_GROUPS = 8;
 size_t fab_doubles(const HcFab& f) { return (size_t)f.nstride * f.ncomp; }
 
-int stage_in(int n, const HcFab* host, const std::vector<int>& comps, Staged& st, cudaStream_t stream) {
-    st.dev.assign(host, host + n);
-    st.bufs.assign(n, nullptr);
-    for (int i = 0; i < n; ++i) {
-        if (!host[i].p) { set_err("null host FAB"); return HC_ERR_ARG; }
-        double* d = nullptr;
-        CUDA_TRY(cudaMallocAsync((void**)&d, fab_doubles(host[i]) * sizeof(double), stream));
-        st.bufs[i] = d; st.dev[i].p = d;
-        for (int c : comps) {
-            if (c >= host[i].ncomp) continue;
-            CUDA_TRY(cudaMemcpyAsync(d + (size_t)c * host[i].nstride, host[i].p + (size_t)c * host[i].nstride,
-                                     (size_t)host[i].nstride * sizeof(double), cudaMemcpyHostToDevice, stream));
-        }
+int host_pipe(int dev, HostPipe*& hp) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    hp = &g_pipe[dev];
+    if (!hp->ready) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&hp->h2d, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&hp->comp, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&hp->d2h, cudaStreamNonBlocking));
+        cudaMemPool_t pool;
+        CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, dev));
+        unsigned long long keep = ~0ull;
+        CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        hp->ready = true;
     }
     return HC_OK;
 }
-int stage_out(int n, const HcFab* host, const std::vector<int>& comps, Staged& st, cudaStream_t stream) {
-    for (int i = 0; i < n; ++i)
-        for (int c : comps) {
-            if (c >= host[i].ncomp) continue;
-            CUDA_TRY(cudaMemcpyAsync(host[i].p + (size_t)c * host[i].nstride, st.bufs[i] + (size_t)c * host[i].nstride,
-                                     (size_t)host[i].nstride * sizeof(double), cudaMemcpyDeviceToHost, stream));
+
+int run_host(int path, int ntiles, std::vector<HostSlot>& slots, const HcBox* tiles, const Consts& k, HcStats* stats) {
+    int dev; if (int rc = current_device(dev)) return rc;
+    HostPipe* hp = nullptr;
+    if (int rc = host_pipe(dev, hp)) return rc;
+    const int nf = (int)slots.size();
+    for (const HostSlot& sl : slots)
+        for (int t = 0; t < ntiles; ++t) if (!sl.host[t].p) { set_err("null host FAB"); return HC_ERR_ARG; }
+    // groups of consecutive tiles with about 1/HOST_GROUPS of the cells each
+    long long total = 0;
+    std::vector<long long> cells(ntiles);
+    for (int t = 0; t < ntiles; ++t) {
+        const HcBox& b = tiles[t];
+        cells[t] = (long long)std::max(0, b.hi[0] - b.lo[0] + 1) * std::max(0, b.hi[1] - b.lo[1] + 1) * std::max(0, b.hi[2] - b.lo[2] + 1);
+        total += cells[t];
+    }
+    const long long per_group = std::max<long long>((total + HOST_GROUPS - 1) / HOST_GROUPS, 1);
+    unsigned long long* dstats = nullptr;
+    CUDA_TRY(cudaMallocAsync((void**)&dstats, 128, hp->comp));
+    CUDA_TRY(cudaMemsetAsync(dstats, 0, 128, hp->comp));
+    std::vector<cudaEvent_t> events;
+    auto new_event = [&](cudaEvent_t& e) { cudaError_t r = cudaEventCreateWithFlags(&e, cudaEventDisableTiming); if (r == cudaSuccess) events.push_back(e); return r; };
+    int rc = HC_OK;
+    std::vector<std::vector<HcFab>> dfab(nf);
+    for (int t0 = 0; t0 < ntiles && rc == HC_OK;) {
+        int t1 = t0; long long acc = 0;
+        while (t1 < ntiles && (t1 == t0 || acc + cells[t1] <= per_group)) acc += cells[t1++];
+        const int n = t1 - t0;
+        std::vector<double*> bufs;
+        for (int s = 0; s < nf; ++s) {
+            dfab[s].assign(slots[s].host + t0, slots[s].host + t1);
+            for (int i = 0; i < n; ++i) {
+                const HcFab& h = slots[s].host[t0 + i];
+                double* d = nullptr;
+                CUDA_TRY(cudaMallocAsync((void**)&d, fab_doubles(h) * sizeof(double), hp->h2d));
+                bufs.push_back(d); dfab[s][i].p = d;
+                for (int c : slots[s].in) {
+                    if (c >= h.ncomp) continue;
+                    CUDA_TRY(cudaMemcpyAsync(d + (size_t)c * h.nstride, h.p + (size_t)c * h.nstride, (size_t)h.nstride * sizeof(double),
+                                             cudaMemcpyHostToDevice, hp->h2d));
+                }
+            }
         }
-    return HC_OK;
-}
-int stage_free(Staged& st, cudaStream_t stream) {
-    for (double* d : st.bufs) if (d) CUDA_TRY(cudaFreeAsync(d, stream));
-    st.bufs.clear();
-    return HC_OK;
+        cudaEvent_t e_in, e_k;
+        CUDA_TRY(new_event(e_in)); CUDA_TRY(new_event(e_k));
+        CUDA_TRY(cudaEventRecord(e_in, hp->h2d));
+        CUDA_TRY(cudaStreamWaitEvent(hp->comp, e_in, 0));
+        std::vector<const HcFab*> fabs(nf);
+        for (int s = 0; s < nf; ++s) fabs[s] = dfab[s].data();
+        rc = launch(path, n, fabs.data(), nf, tiles + t0, k, nullptr, nullptr, hp->comp, dstats);
+        if (rc != HC_OK) break;
+        CUDA_TRY(cudaEventRecord(e_k, hp->comp));
+        CUDA_TRY(cudaStreamWaitEvent(hp->d2h, e_k, 0));
+        for (int s = 0; s < nf; ++s)
+            for (int i = 0; i < n; ++i) {
+                const HcFab& h = slots[s].host[t0 + i];
+                for (int c : slots[s].out) {
+                    if (c >= h.ncomp) continue;
+                    CUDA_TRY(cudaMemcpyAsync(h.p + (size_t)c * h.nstride, dfab[s][i].p + (size_t)c * h.nstride, (size_t)h.nstride * sizeof(double),
+                                             cudaMemcpyDeviceToHost, hp->d2h));
+                }
+            }
+        for (double* d : bufs) CUDA_TRY(cudaFreeAsync(d, hp->d2h));
+        t0 = t1;
+    }
+    if (rc == HC_OK && stats) CUDA_TRY(cudaMemcpyAsync(stats, dstats, sizeof(HcStats), cudaMemcpyDeviceToHost, hp->comp));
+    CUDA_TRY(cudaFreeAsync(dstats, hp->comp));
+    CUDA_TRY(cudaStreamSynchronize(hp->comp));
+    CUDA_TRY(cudaStreamSynchronize(hp->d2h));
+    for (cudaEvent_t e : events) cudaEventDestroy(e);
+    return rc;
 }
 
 }  // namespace
@@ -668,42 +736,32 @@ int hc_eos_T_given_Re(const HcFab* state, const HcFab* diag, HcBox tile, double 
 
 int hc_integrate_vec_host(int ntiles, const HcFab* state, const HcFab* diag, const HcBox* tiles, double a, double dt,
                           const HcParams* prm, HcStats* stats) {
-    if (ntiles <= 0 || !state || !diag || !tiles) { set_err("bad argument"); return HC_ERR_ARG; }
-    cudaStream_t s = nullptr;
-    Staged S, D;
-    if (int rc = stage_in(ntiles, state, {DENS, EDEN, EINT}, S, s)) return rc;
-    if (int rc = stage_in(ntiles, diag, {TEMP, NE}, D, s)) return rc;
-    int rc = hc_integrate_vec_batch(ntiles, S.dev.data(), D.dev.data(), tiles, a, dt, prm, stats, nullptr, s);
-    if (rc == HC_OK) rc = stage_out(ntiles, state, {EDEN, EINT}, S, s);
-    if (rc == HC_OK) rc = stage_out(ntiles, diag, {TEMP, NE}, D, s);
-    stage_free(S, s); stage_free(D, s);
-    if (rc == HC_OK) CUDA_TRY(cudaStreamSynchronize(s));
-    return rc;
+    if (ntiles <= 0 || !state || !diag || !tiles || !valid_params(prm) || !(a > 0.0)) { set_err("bad argument"); return HC_ERR_ARG; }
+    if (g_rates.empty()) { set_err("hc_tables_upload has not been called"); return HC_ERR_NO_TABLES; }
+    if (stats) std::memset(stats, 0, sizeof *stats);
+    const Consts k = make_consts_vec(g_rates.data(), *prm, a, dt);
+    std::vector<HostSlot> slots = {{state, {DENS, EDEN, EINT}, {EDEN, EINT}}, {diag, {TEMP, NE}, {TEMP, NE}}};
+    return run_host(PATH_VEC, ntiles, slots, tiles, k, stats);
 }
 
 int hc_integrate_struct_host(int ntiles, const HcFab* s_old, const HcFab* diag, const HcFab* s_new, const HcFab* hydro_src,
                              const HcFab* reset_src, const HcFab* ir, const HcBox* tiles, double a, double a_end, double dt,
                              int sdc_iter, const HcParams* prm, HcStats* stats) {
-    if (ntiles <= 0 || !s_old || !diag || !s_new || !hydro_src || !reset_src || !ir || !tiles) { set_err("bad argument"); return HC_ERR_ARG; }
-    cudaStream_t s = nullptr;
-    Staged SO, D, SN, H, R, I;
-    const bool inhomo = prm && prm->inhomo_reion;
-    int rc = stage_in(ntiles, s_old, {DENS, EDEN, EINT}, SO, s);
-    if (rc == HC_OK) rc = stage_in(ntiles, diag, inhomo ? std::vector<int>{TEMP, NE, ZHI} : std::vector<int>{TEMP, NE}, D, s);
-    if (rc == HC_OK) rc = stage_in(ntiles, s_new, {DENS, EDEN, EINT}, SN, s);
-    if (rc == HC_OK) rc = stage_in(ntiles, hydro_src, {DENS, EINT}, H, s);
-    if (rc == HC_OK) rc = stage_in(ntiles, reset_src, {0}, R, s);
-    if (rc == HC_OK) rc = stage_in(ntiles, ir, {}, I, s);
-    if (rc == HC_OK) rc = hc_integrate_struct_batch(ntiles, SO.dev.data(), D.dev.data(), SN.dev.data(), H.dev.data(), R.dev.data(), I.dev.data(),
-                                                    tiles, a, a_end, dt, sdc_iter, prm, stats, nullptr, s);
-    if (rc == HC_OK) {
-        if (sdc_iter >= 0) { rc = stage_out(ntiles, s_new, {EDEN, EINT}, SN, s); if (rc == HC_OK) rc = stage_out(ntiles, ir, {0}, I, s); }
-        else rc = stage_out(ntiles, s_old, {EDEN, EINT}, SO, s);
+    if (ntiles <= 0 || !s_old || !diag || !s_new || !hydro_src || !reset_src || !ir || !tiles || !valid_params(prm) || !(a > 0.0) || !(a_end > 0.0)) {
+        set_err("bad argument"); return HC_ERR_ARG;
     }
-    if (rc == HC_OK) rc = stage_out(ntiles, diag, {TEMP, NE}, D, s);
-    stage_free(SO, s); stage_free(D, s); stage_free(SN, s); stage_free(H, s); stage_free(R, s); stage_free(I, s);
-    if (rc == HC_OK) CUDA_TRY(cudaStreamSynchronize(s));
-    return rc;
+    if (g_rates.empty()) { set_err("hc_tables_upload has not been called"); return HC_ERR_NO_TABLES; }
+    if (stats) std::memset(stats, 0, sizeof *stats);
+    const Consts k = make_consts_struct(g_rates.data(), *prm, a, a_end, dt, sdc_iter);
+    const bool src = (sdc_iter >= 0);   // with sdc_iter < 0 the update goes to S_old (f_rhs_struct.H:430-444 mirrored in store_cell)
+    std::vector<HostSlot> slots = {
+        {s_old, {DENS, EDEN, EINT}, src ? std::vector<int>{} : std::vector<int>{EDEN, EINT}},
+        {diag, prm->inhomo_reion ? std::vector<int>{TEMP, NE, ZHI} : std::vector<int>{TEMP, NE}, {TEMP, NE}},
+        {s_new, {DENS, EDEN, EINT}, src ? std::vector<int>{EDEN, EINT} : std::vector<int>{}},
+        {hydro_src, {DENS, EINT}, {}},
+        {reset_src, {0}, {}},
+        {ir, {}, src ? std::vector<int>{0} : std::vector<int>{}}};
+    return run_host(PATH_STRUCT, ntiles, slots, tiles, k, stats);
 }
 
 int hc_measure_fp64_peak(double* flops_per_s) {
