@@ -124,6 +124,9 @@ def cpu_reference_run(args, boxes_idx, boxes, budget_s, repeat=1):
     kind, cores, ref, port = "reference", 1, None, None
     try:
         ref = pyref.Reference("omp")
+        # all the host threads the box offers (torchrun exports OMP_NUM_THREADS=1 to its children; NYX_REF_THREADS overrides)
+        want = int(os.environ.get("NYX_REF_THREADS", "0")) or len(os.sched_getaffinity(0))
+        ref.set("omp.num_threads", want)
         cores = ref.max_threads()
     except (FileNotFoundError, OSError):
         kind = "port"
