@@ -10,8 +10,9 @@
  *   hc_integrate_vec[_batch]               <- Nyx::integrate_state_vec_mfin  Source/HeatCool/integrate_state_vec_3d.cpp:72-365
  *                                             (callers integrate_state_vec :44-70, integrate_state_grownvec :367-396)
  *   hc_integrate_struct[_batch]            <- Nyx::integrate_state_struct_mfin Source/HeatCool/integrate_state_with_source_3d.cpp:187-709
- *   hc_eos_T_given_Re                      <- nyx_eos_T_given_Re_device over a box, the body of Nyx::compute_new_temp
- *                                             Source/EOS/eos_hc.H:190-220, Source/Driver/Nyx.cpp:2473-2490
+ *   hc_eos_T_given_Re                      <- nyx_eos_T_given_Re_device over a box  Source/EOS/eos_hc.H:190-220
+ *   hc_compute_new_temp_batch              <- Nyx::compute_new_temp                 Source/Driver/Nyx.cpp:2435-2522
+ *   hc_reset_internal_energy_batch         <- Nyx::reset_internal_energy            Source/Driver/Nyx.cpp:2356-2385, Source/EOS/reset_internal_e.H:16-68
  *   HcParams                               <- the nyx.* run-time flags of the path, Source/Driver/Nyx.cpp:116-181,
  *                                             Source/HeatCool/f_rhs_struct.H:45-101
  *   HcStats                                <- CVodeGetNum* counters (integrate_state_with_source_3d.cpp:755-790) and the
@@ -134,6 +135,17 @@ int hc_integrate_struct_batch(int ntiles, const HcFab* s_old, const HcFab* diag,
 int hc_eos_T_given_Re(const HcFab* state, const HcFab* diag, HcBox tile, double a, const HcParams* prm, HcStats* stats,
                       void* stream);
 
+/* Nyx::compute_new_temp, the cell loop (Source/Driver/Nyx.cpp:2435-2522): for every cell of every tile, rho_e > 0: T, ne from the EOS at
+ * e = rho_e * (1 / rho), clipped to large_temp when max_temp_dt == 1 (then rho_e, rho_E are rewritten); rho_e <= 0: T = small_temp, e from
+ * nyx_eos_given_RT with the cell's current ne, rho_e and rho_E rewritten.  stats (may be NULL): n_cells, sum_eos, sum_ne_iters,
+ * n_floor = cells reset to small_temp, n_failed = cells clipped at large_temp. */
+int hc_compute_new_temp_batch(int ntiles, const HcFab* state, const HcFab* diag, const HcBox* tiles, double a, const HcParams* prm,
+                              double small_temp, double large_temp, int max_temp_dt, HcStats* stats, void* stream);
+/* Nyx::reset_internal_energy, the cell loop (Source/Driver/Nyx.cpp:2356-2385 with reset_internal_e, Source/EOS/reset_internal_e.H:16-68);
+ * reset_src is the one-component reset_e_src FAB */
+int hc_reset_internal_energy_batch(int ntiles, const HcFab* state, const HcFab* diag, const HcFab* reset_src, const HcBox* tiles, double a,
+                                   const HcParams* prm, double small_temp, int interp, void* stream);
+
 /* Host-buffer variants for CPU builds of the host application (and the end-to-end bench): same semantics,
  * HcFab.p are HOST pointers; the call stages H2D, runs, and stages the mutated components D2H. */
 int hc_integrate_vec_host(int ntiles, const HcFab* state, const HcFab* diag, const HcBox* tiles, double a, double dt,
@@ -141,6 +153,11 @@ int hc_integrate_vec_host(int ntiles, const HcFab* state, const HcFab* diag, con
 int hc_integrate_struct_host(int ntiles, const HcFab* s_old, const HcFab* diag, const HcFab* s_new, const HcFab* hydro_src,
                              const HcFab* reset_src, const HcFab* ir, const HcBox* tiles, double a, double a_end, double dt,
                              int sdc_iter, const HcParams* prm, HcStats* stats);
+
+int hc_compute_new_temp_host(int ntiles, const HcFab* state, const HcFab* diag, const HcBox* tiles, double a, const HcParams* prm,
+                             double small_temp, double large_temp, int max_temp_dt, HcStats* stats);
+int hc_reset_internal_energy_host(int ntiles, const HcFab* state, const HcFab* diag, const HcFab* reset_src, const HcBox* tiles, double a,
+                                  const HcParams* prm, double small_temp, int interp);
 
 /* measured FP64 FMA throughput of the current device in FLOP/s (2 flops per DFMA), for roofline denominators */
 int hc_measure_fp64_peak(double* flops_per_s);

@@ -98,6 +98,10 @@ def declare(lib, prefix="hc_"):
     lib.hc_integrate_struct_batch.argtypes = [C.c_int] + [fp] * 6 + [bp, C.c_double, C.c_double, C.c_double, C.c_int, pp, sp,
                                                                       C.c_void_p, C.c_void_p]
     lib.hc_eos_T_given_Re.argtypes = [fp, fp, HcBox, C.c_double, pp, sp, C.c_void_p]
+    lib.hc_compute_new_temp_batch.argtypes = [C.c_int, fp, fp, bp, C.c_double, pp, C.c_double, C.c_double, C.c_int, sp, C.c_void_p]
+    lib.hc_reset_internal_energy_batch.argtypes = [C.c_int, fp, fp, fp, bp, C.c_double, pp, C.c_double, C.c_int, C.c_void_p]
+    lib.hc_compute_new_temp_host.argtypes = [C.c_int, fp, fp, bp, C.c_double, pp, C.c_double, C.c_double, C.c_int, sp]
+    lib.hc_reset_internal_energy_host.argtypes = [C.c_int, fp, fp, fp, bp, C.c_double, pp, C.c_double, C.c_int]
     lib.hc_integrate_vec_host.argtypes = [C.c_int, fp, fp, bp, C.c_double, C.c_double, pp, sp]
     lib.hc_integrate_struct_host.argtypes = [C.c_int] + [fp] * 6 + [bp, C.c_double, C.c_double, C.c_double, C.c_int, pp, sp]
     lib.hc_measure_fp64_peak.argtypes = [_dp]
@@ -193,6 +197,18 @@ class NyxHC:
         v = C.c_double()
         self.check(self.lib.hc_measure_fp64_peak(C.byref(v)))
         return v.value
+
+    def compute_new_temp_batch(self, state_fabs, diag_fabs, tiles, a, small_temp, large_temp, max_temp_dt, params=None, stream=None):
+        p = params or self.default_params()
+        st = HcStats()
+        self.check(self.lib.hc_compute_new_temp_batch(len(tiles), self._arr(state_fabs, HcFab), self._arr(diag_fabs, HcFab), self._arr(tiles, HcBox),
+                                                      a, C.byref(p), small_temp, large_temp, max_temp_dt, C.byref(st), stream))
+        return st
+
+    def reset_internal_energy_batch(self, state_fabs, diag_fabs, reset_fabs, tiles, a, small_temp, interp=0, params=None, stream=None):
+        p = params or self.default_params()
+        self.check(self.lib.hc_reset_internal_energy_batch(len(tiles), self._arr(state_fabs, HcFab), self._arr(diag_fabs, HcFab),
+                                                           self._arr(reset_fabs, HcFab), self._arr(tiles, HcBox), a, C.byref(p), small_temp, interp, stream))
 
     def selftest_log10(self, x):
         """log10 of a float64 array through the kernels' table-driven fast path -> (y, bad)"""

@@ -124,6 +124,10 @@ struct KernelArgs {
     const double* iony;
     const double* cool;
     const double* logtab;
+    // hc_eos_kernel / hc_reset_e_kernel only
+    int eos_mode;             // 0: T, ne from (rho, e = rho_e / rho);  1: the cell body of Nyx::compute_new_temp
+    int max_temp_dt, interp;
+    double small_temp, large_temp;
 };
 
 enum StatSlot { S_CELLS = 0, S_FAILED, S_FLOOR, S_NST, S_MAXNST, S_NFE, S_NFELS, S_NETF, S_NNI, S_NCFN, S_NSETUPS, S_NEITERS, S_ATTEMPTS, S_EOS, S_COUNT };
@@ -342,7 +346,11 @@ __global__ void __launch_bounds__(THREADS, 1) hc_integrate_kernel(const __grid_c
     flush_totals(tot, s_stats, a.dstats);
 }
 
-// compute_new_temp core: one thread per cell, grid-stride over x-rows; same table staging
+// EOS kernel: one thread per cell, grid-stride over the cells of one tile; ionization tables staged in shared memory.
+//   eos_mode 0: diag(Temp, Ne) = nyx_eos_T_given_Re(rho, rho_e / rho)                       (eos_hc.H:204-220)
+//   eos_mode 1: the cell body of Nyx::compute_new_temp (Source/Driver/Nyx.cpp:2473-2519): e = rho_e * (1 / rho); cells at or above
+//               large_temp are clipped (max_temp_dt), cells with rho_e <= 0 are reset to small_temp; both rewrite (rho e, rho E).
+// dstats: S_CELLS, S_EOS, S_NEITERS as for the integrators; S_FLOOR counts the cells reset to small_temp, S_FAILED the clipped ones.
 __global__ void __launch_bounds__(THREADS, 1) hc_eos_kernel(const __grid_constant__ KernelArgs a) {
     __shared__ unsigned long long s_stats[S_COUNT];
     double* s_ionx = reinterpret_cast<double*>(s_raw);
@@ -352,31 +360,104 @@ __global__ void __launch_bounds__(THREADS, 1) hc_eos_kernel(const __grid_constan
     __syncthreads();
     const Tables tb{s_ionx, s_iony, a.cool, a.logtab};
     const Consts& c = a.k;
-    unsigned long long iters = 0, cells = 0;
+    unsigned long long iters = 0, cells = 0, n_eos = 0, n_small = 0, n_large = 0;
     const TileDesc& t = a.tiles[0];
     const long long plane = (long long)t.nx * t.ny;
+    const HcFab& S = t.f[F_STATE];
+    const HcFab& D = t.f[F_DIAG];
     for (long long id = (long long)blockIdx.x * THREADS + threadIdx.x; id < a.ncells; id += (long long)gridDim.x * THREADS) {
         const int kk = (int)(id / plane);
         const int rem = (int)(id - (long long)kk * plane);
         const int jj = rem / t.nx;
         const int i = t.lo[0] + (rem - jj * t.nx), j = t.lo[1] + jj, k = t.lo[2] + kk;
-        const long long so = fab_off(t.f[F_STATE], i, j, k), dof = fab_off(t.f[F_DIAG], i, j, k);
-        const double R = t.f[F_STATE].p[so + DENS * t.f[F_STATE].nstride];
-        const double e = t.f[F_STATE].p[so + EINT * t.f[F_STATE].nstride] / R;
-        const double rho_cgs = R * density_to_cgs / c.a3_eos;
-        const double U = e * e_to_cgs;
-        const double nh = rho_cgs * c.h_species / MPROTON;
-        EosOut s;
-        iterate_ne(tb, c, c.uvb_eos, 1.0, 1.0, U, nh, s);
-        t.f[F_DIAG].p[dof + TEMP * t.f[F_DIAG].nstride] = s.T;
-        t.f[F_DIAG].p[dof + NE * t.f[F_DIAG].nstride] = s.ne;
-        iters += s.iters; cells++;
+        const long long so = fab_off(S, i, j, k), dof = fab_off(D, i, j, k);
+        const double R = S.p[so + DENS * S.nstride];
+        const double rhoe = S.p[so + EINT * S.nstride];
+        cells++;
+        if (a.eos_mode == 0 || rhoe > 0.0) {
+            const double e = (a.eos_mode == 0) ? rhoe / R : rhoe * (1.0 / R);
+            const double rho_cgs = R * density_to_cgs / c.a3_eos;
+            const double U = e * e_to_cgs;
+            const double nh = rho_cgs * c.h_species / MPROTON;
+            EosOut s;
+            iterate_ne(tb, c, c.uvb_eos, 1.0, 1.0, U, nh, s);
+            iters += s.iters; n_eos++;
+            double T = s.T;
+            if (a.eos_mode == 1 && T >= a.large_temp && a.max_temp_dt == 1) {   // Nyx.cpp:2488-2505
+                T = a.large_temp;
+                const double mu = c.c_mu_num / (c.c_mu_den + s.ne);             // nyx_eos_given_RT, eos_hc.H:222-231
+                const double eint = T / (c.gm1 * mp_over_kb * mu);
+                const double rhoInv = 1.0 / R;
+                const double mx = S.p[so + 1 * S.nstride], my = S.p[so + 2 * S.nstride], mz = S.p[so + 3 * S.nstride];
+                const double ke = 0.5e0 * (mx * mx + my * my + mz * mz) * rhoInv;
+                const double re = R * eint;
+                S.p[so + EINT * S.nstride] = re;
+                S.p[so + EDEN * S.nstride] = re + ke;
+                n_large++;
+            }
+            D.p[dof + TEMP * D.nstride] = T;
+            D.p[dof + NE * D.nstride] = s.ne;
+        } else {   // Nyx.cpp:2507-2519: rho e <= 0 -> small_temp with the cell's current ne
+            const double ne_old = D.p[dof + NE * D.nstride];
+            const double mu = c.c_mu_num / (c.c_mu_den + ne_old);
+            const double eint = a.small_temp / (c.gm1 * mp_over_kb * mu);
+            const double rhoInv = 1.0 / R;
+            const double mx = S.p[so + 1 * S.nstride], my = S.p[so + 2 * S.nstride], mz = S.p[so + 3 * S.nstride];
+            const double ke = 0.5e0 * (mx * mx + my * my + mz * mz) * rhoInv;
+            const double re = R * eint;
+            D.p[dof + TEMP * D.nstride] = a.small_temp;
+            S.p[so + EINT * S.nstride] = re;
+            S.p[so + EDEN * S.nstride] = re + ke;
+            n_small++;
+        }
     }
     atomicAdd(&s_stats[S_CELLS], cells);
-    atomicAdd(&s_stats[S_EOS], cells);
+    atomicAdd(&s_stats[S_EOS], n_eos);
     atomicAdd(&s_stats[S_NEITERS], iters);
+    if (n_small) atomicAdd(&s_stats[S_FLOOR], n_small);
+    if (n_large) atomicAdd(&s_stats[S_FAILED], n_large);
     __syncthreads();
     if (threadIdx.x < S_COUNT) atomicAdd(&a.dstats[threadIdx.x], s_stats[threadIdx.x]);
+}
+
+// reset_internal_e (Source/EOS/reset_internal_e.H:16-68) over one tile: synchronises (rho e) and (rho E), records the change of
+// (rho e) in the reset source.  Pure streaming: 8 doubles read, up to 3 written per cell.
+__global__ void __launch_bounds__(256) hc_reset_e_kernel(const __grid_constant__ KernelArgs a) {
+    const Consts& c = a.k;
+    const TileDesc& t = a.tiles[0];
+    const long long plane = (long long)t.nx * t.ny;
+    const HcFab& U = t.f[F_STATE];
+    const HcFab& D = t.f[F_DIAG];
+    const HcFab& Rs = t.f[2];
+    for (long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x; id < a.ncells; id += (long long)gridDim.x * blockDim.x) {
+        const int kk = (int)(id / plane);
+        const int rem = (int)(id - (long long)kk * plane);
+        const int jj = rem / t.nx;
+        const int i = t.lo[0] + (rem - jj * t.nx), j = t.lo[1] + jj, k = t.lo[2] + kk;
+        const long long so = fab_off(U, i, j, k);
+        double* pr = Rs.p + fab_off(Rs, i, j, k);
+        const double rho = U.p[so + DENS * U.nstride];
+        const double rhoInv = 1.0 / rho;
+        const double Up = U.p[so + 1 * U.nstride] * rhoInv, Vp = U.p[so + 2 * U.nstride] * rhoInv, Wp = U.p[so + 3 * U.nstride] * rhoInv;
+        const double ke = 0.5 * rho * (Up * Up + Vp * Vp + Wp * Wp);
+        const double eden = U.p[so + EDEN * U.nstride], eint = U.p[so + EINT * U.nstride];
+        const double rho_eint = eden - ke;
+        if (rho_eint > 0.0 && rho_eint / eden > 1.0e-6 && a.interp == 0) {
+            *pr = rho_eint - eint;
+            U.p[so + EINT * U.nstride] = rho_eint;
+        } else if (eint > 0.0) {
+            *pr += 0.0;
+            U.p[so + EDEN * U.nstride] = eint + ke;
+        } else if (eint <= 0.0) {
+            const double ne = D.p[fab_off(D, i, j, k) + NE * D.nstride];
+            const double mu = c.c_mu_num / (c.c_mu_den + ne);
+            const double eint_new = a.small_temp / (c.gm1 * mp_over_kb * mu);
+            const double re = rho * eint_new;
+            *pr = re - eint;
+            U.p[so + EINT * U.nstride] = re;
+            U.p[so + EDEN * U.nstride] = re + ke;
+        }
+    }
 }
 
 #include "hc_sorted.cuh"
@@ -468,8 +549,14 @@ int set_smem_attr(KernelT kernel, DeviceTables& dt, int slot, size_t bytes) {
 
 // Common launcher: build tile descriptors, stream-ordered scratch, launch, optionally read the statistics back.
 // `ext_dstats` (device, 14 x u64, zeroed by the caller): accumulate the statistics there instead (several launches of one call).
+struct EosOpts {
+    int mode = 0, max_temp_dt = 0, interp = 0;
+    double small_temp = 0.0, large_temp = 0.0;
+};
+constexpr int PATH_RESET_E = 3;   // hc_reset_e_kernel (PATH_EOS = 2: hc_eos_kernel); both take ONE tile per launch
+
 int launch(int path, int ntiles, const HcFab* const* fabs, int nf, const HcBox* tiles, const Consts& k, HcStats* stats,
-           HcCellStat* cell_stats, cudaStream_t stream, unsigned long long* ext_dstats = nullptr) {
+           HcCellStat* cell_stats, cudaStream_t stream, unsigned long long* ext_dstats = nullptr, const EosOpts* eos = nullptr) {
     int dev; if (int rc = current_device(dev)) return rc;
     DeviceTables& dt = g_dev[dev];
     if (!dt.ionx) { set_err("hc_tables_upload has not been called on device %d", dev); return HC_ERR_NO_TABLES; }
@@ -504,6 +591,7 @@ int launch(int path, int ntiles, const HcFab* const* fabs, int nf, const HcBox* 
     a.dstats = ext_dstats ? ext_dstats : reinterpret_cast<unsigned long long*>(scratch + 64);
     a.cell_stats = cell_stats;
     a.ionx = dt.ionx; a.iony = dt.iony; a.cool = dt.cool; a.logtab = dt.logtab;
+    if (eos) { a.eos_mode = eos->mode; a.max_temp_dt = eos->max_temp_dt; a.interp = eos->interp; a.small_temp = eos->small_temp; a.large_temp = eos->large_temp; }
 
     const long long want = (ncells + THREADS - 1) / THREADS;
     const int grid = (int)std::min<long long>(want, dt.sm_count);
@@ -527,8 +615,13 @@ int launch(int path, int ntiles, const HcFab* const* fabs, int nf, const HcBox* 
         hc_integrate_kernel<PATH_STRUCT><<<grid, THREADS, SMEM_INTEGRATE, stream>>>(a);
     } else {
 #endif
-        if (int rc = set_smem_attr(hc_eos_kernel, dt, 2, SMEM_EOS)) return rc;
-        hc_eos_kernel<<<grid, THREADS, SMEM_EOS, stream>>>(a);
+        if (path == PATH_RESET_E) {
+            const int g = (int)std::min<long long>((ncells + 255) / 256, (long long)dt.sm_count * 8);
+            hc_reset_e_kernel<<<g, 256, 0, stream>>>(a);
+        } else {
+            if (int rc = set_smem_attr(hc_eos_kernel, dt, 2, SMEM_EOS)) return rc;
+            hc_eos_kernel<<<grid, THREADS, SMEM_EOS, stream>>>(a);
+        }
     }
     CUDA_TRY(cudaGetLastError());
     if (stats && !ext_dstats) {
@@ -573,7 +666,7 @@ int host_pipe(int dev, HostPipe*& hp) {
     return HC_OK;
 }
 
-int run_host(int path, int ntiles, std::vector<HostSlot>& slots, const HcBox* tiles, const Consts& k, HcStats* stats) {
+int run_host(int path, int ntiles, std::vector<HostSlot>& slots, const HcBox* tiles, const Consts& k, HcStats* stats, const EosOpts* eos = nullptr) {
     int dev; if (int rc = current_device(dev)) return rc;
     HostPipe* hp = nullptr;
     if (int rc = host_pipe(dev, hp)) return rc;
@@ -621,7 +714,15 @@ int run_host(int path, int ntiles, std::vector<HostSlot>& slots, const HcBox* ti
         CUDA_TRY(cudaStreamWaitEvent(hp->comp, e_in, 0));
         std::vector<const HcFab*> fabs(nf);
         for (int s = 0; s < nf; ++s) fabs[s] = dfab[s].data();
-        rc = launch(path, n, fabs.data(), nf, tiles + t0, k, nullptr, nullptr, hp->comp, dstats);
+        if (path == PATH_EOS || path == PATH_RESET_E) {   // one tile per launch
+            for (int i = 0; i < n && rc == HC_OK; ++i) {
+                std::vector<const HcFab*> one(nf);
+                for (int s = 0; s < nf; ++s) one[s] = dfab[s].data() + i;
+                rc = launch(path, 1, one.data(), nf, tiles + t0 + i, k, nullptr, nullptr, hp->comp, dstats, eos);
+            }
+        } else {
+            rc = launch(path, n, fabs.data(), nf, tiles + t0, k, nullptr, nullptr, hp->comp, dstats);
+        }
         if (rc != HC_OK) break;
         CUDA_TRY(cudaEventRecord(e_k, hp->comp));
         CUDA_TRY(cudaStreamWaitEvent(hp->d2h, e_k, 0));
@@ -734,6 +835,49 @@ int hc_eos_T_given_Re(const HcFab* state, const HcFab* diag, HcBox tile, double 
     return launch(PATH_EOS, 1, fabs, 2, &tile, k, stats, nullptr, (cudaStream_t)stream);
 }
 
+namespace {
+// the one-tile-per-launch kernels over a list of tiles: statistics accumulate in one device buffer
+int launch_each(int path, int ntiles, const HcFab* const* fabs, int nf, const HcBox* tiles, const Consts& k, const EosOpts& eos, HcStats* stats,
+                cudaStream_t stream) {
+    if (stats) std::memset(stats, 0, sizeof *stats);
+    unsigned long long* dstats = nullptr;
+    CUDA_TRY(cudaMallocAsync((void**)&dstats, 128, stream));
+    CUDA_TRY(cudaMemsetAsync(dstats, 0, 128, stream));
+    int rc = HC_OK;
+    for (int t = 0; t < ntiles && rc == HC_OK; ++t) {
+        const HcFab* one[6];
+        for (int s = 0; s < nf; ++s) one[s] = fabs[s] + t;
+        rc = launch(path, 1, one, nf, tiles + t, k, nullptr, nullptr, stream, dstats, &eos);
+    }
+    if (rc == HC_OK && stats) {
+        CUDA_TRY(cudaMemcpyAsync(stats, dstats, sizeof(HcStats), cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));
+    }
+    CUDA_TRY(cudaFreeAsync(dstats, stream));
+    return rc;
+}
+}  // namespace
+
+int hc_compute_new_temp_batch(int ntiles, const HcFab* state, const HcFab* diag, const HcBox* tiles, double a, const HcParams* prm,
+                              double small_temp, double large_temp, int max_temp_dt, HcStats* stats, void* stream) {
+    if (!valid_params(prm) || ntiles < 0 || (ntiles > 0 && (!state || !diag || !tiles)) || !(a > 0.0)) { set_err("bad argument"); return HC_ERR_ARG; }
+    if (g_rates.empty()) { set_err("hc_tables_upload has not been called"); return HC_ERR_NO_TABLES; }
+    const Consts k = make_consts_eos(g_rates.data(), *prm, a);
+    EosOpts eos; eos.mode = 1; eos.small_temp = small_temp; eos.large_temp = large_temp; eos.max_temp_dt = max_temp_dt;
+    const HcFab* fabs[2] = {state, diag};
+    return launch_each(PATH_EOS, ntiles, fabs, 2, tiles, k, eos, stats, (cudaStream_t)stream);
+}
+
+int hc_reset_internal_energy_batch(int ntiles, const HcFab* state, const HcFab* diag, const HcFab* reset_src, const HcBox* tiles, double a,
+                                   const HcParams* prm, double small_temp, int interp, void* stream) {
+    if (!valid_params(prm) || ntiles < 0 || (ntiles > 0 && (!state || !diag || !reset_src || !tiles)) || !(a > 0.0)) { set_err("bad argument"); return HC_ERR_ARG; }
+    if (g_rates.empty()) { set_err("hc_tables_upload has not been called"); return HC_ERR_NO_TABLES; }
+    const Consts k = make_consts_eos(g_rates.data(), *prm, a);
+    EosOpts eos; eos.small_temp = small_temp; eos.interp = interp;
+    const HcFab* fabs[3] = {state, diag, reset_src};
+    return launch_each(PATH_RESET_E, ntiles, fabs, 3, tiles, k, eos, nullptr, (cudaStream_t)stream);
+}
+
 int hc_integrate_vec_host(int ntiles, const HcFab* state, const HcFab* diag, const HcBox* tiles, double a, double dt,
                           const HcParams* prm, HcStats* stats) {
     if (ntiles <= 0 || !state || !diag || !tiles || !valid_params(prm) || !(a > 0.0)) { set_err("bad argument"); return HC_ERR_ARG; }
@@ -762,6 +906,27 @@ int hc_integrate_struct_host(int ntiles, const HcFab* s_old, const HcFab* diag, 
         {reset_src, {0}, {}},
         {ir, {}, src ? std::vector<int>{0} : std::vector<int>{}}};
     return run_host(PATH_STRUCT, ntiles, slots, tiles, k, stats);
+}
+
+int hc_compute_new_temp_host(int ntiles, const HcFab* state, const HcFab* diag, const HcBox* tiles, double a, const HcParams* prm,
+                             double small_temp, double large_temp, int max_temp_dt, HcStats* stats) {
+    if (ntiles <= 0 || !state || !diag || !tiles || !valid_params(prm) || !(a > 0.0)) { set_err("bad argument"); return HC_ERR_ARG; }
+    if (g_rates.empty()) { set_err("hc_tables_upload has not been called"); return HC_ERR_NO_TABLES; }
+    if (stats) std::memset(stats, 0, sizeof *stats);
+    const Consts k = make_consts_eos(g_rates.data(), *prm, a);
+    EosOpts eos; eos.mode = 1; eos.small_temp = small_temp; eos.large_temp = large_temp; eos.max_temp_dt = max_temp_dt;
+    std::vector<HostSlot> slots = {{state, {0, 1, 2, 3, EDEN, EINT}, {EDEN, EINT}}, {diag, {TEMP, NE}, {TEMP, NE}}};
+    return run_host(PATH_EOS, ntiles, slots, tiles, k, stats, &eos);
+}
+
+int hc_reset_internal_energy_host(int ntiles, const HcFab* state, const HcFab* diag, const HcFab* reset_src, const HcBox* tiles, double a,
+                                  const HcParams* prm, double small_temp, int interp) {
+    if (ntiles <= 0 || !state || !diag || !reset_src || !tiles || !valid_params(prm) || !(a > 0.0)) { set_err("bad argument"); return HC_ERR_ARG; }
+    if (g_rates.empty()) { set_err("hc_tables_upload has not been called"); return HC_ERR_NO_TABLES; }
+    const Consts k = make_consts_eos(g_rates.data(), *prm, a);
+    EosOpts eos; eos.small_temp = small_temp; eos.interp = interp;
+    std::vector<HostSlot> slots = {{state, {0, 1, 2, 3, EDEN, EINT}, {EDEN, EINT}}, {diag, {NE}, {}}, {reset_src, {0}, {0}}};
+    return run_host(PATH_RESET_E, ntiles, slots, tiles, k, nullptr, &eos);
 }
 
 int hc_measure_fp64_peak(double* flops_per_s) {

@@ -181,3 +181,41 @@ int Nyx::integrate_state_struct_mfin(Array4<Real> const& state4, Array4<Real> co
     std::vector<HcBox> t{to_box(tbx)};
     return struct_batch(f, t, a, a_end, delta_time, sdc_iter, old_max_steps, new_max_steps);
 }
+
+
+// ---- next rows of the path: the cell loops of Nyx::compute_new_temp (Source/Driver/Nyx.cpp:2435-2522) and
+// Nyx::reset_internal_energy (:2356-2385).  Both methods live in Nyx.cpp next to unrelated code, so they are offered as free functions
+// that the method bodies call (INTEGRATION.md shows the two-line patch); `a` = get_comoving_a(state[State_Type].curTime()),
+// small_temp / large_temp / max_temp_dt are the Nyx statics of the same names.
+void nyx_hc_compute_new_temp(MultiFab& S_new, MultiFab& D_new, Real a, Real small_temp, Real large_temp, int max_temp_dt)
+{
+    std::vector<HcFab> s, d; std::vector<HcBox> t;
+    for (MFIter mfi(S_new); mfi.isValid(); ++mfi) {
+        s.push_back(to_fab(S_new.array(mfi))); d.push_back(to_fab(D_new.array(mfi))); t.push_back(to_box(mfi.validbox()));
+    }
+    if (t.empty()) return;
+    const HcParams p = params_from_nyx(Nyx::old_max_sundials_steps);
+    HcStats st{};
+#ifdef AMREX_USE_GPU
+    check(hc_compute_new_temp_batch((int)t.size(), s.data(), d.data(), t.data(), a, &p, small_temp, large_temp, max_temp_dt, &st, nullptr));
+#else
+    check(hc_compute_new_temp_host((int)t.size(), s.data(), d.data(), t.data(), a, &p, small_temp, large_temp, max_temp_dt, &st));
+#endif
+    g_last_stats = st;
+}
+
+void nyx_hc_reset_internal_energy(MultiFab& S_new, MultiFab& D_new, MultiFab& reset_e_src, Real a, Real small_temp, int interp)
+{
+    std::vector<HcFab> s, d, r; std::vector<HcBox> t;
+    for (MFIter mfi(S_new); mfi.isValid(); ++mfi) {
+        s.push_back(to_fab(S_new.array(mfi))); d.push_back(to_fab(D_new.array(mfi))); r.push_back(to_fab(reset_e_src.array(mfi)));
+        t.push_back(to_box(mfi.validbox()));
+    }
+    if (t.empty()) return;
+    const HcParams p = params_from_nyx(Nyx::old_max_sundials_steps);
+#ifdef AMREX_USE_GPU
+    check(hc_reset_internal_energy_batch((int)t.size(), s.data(), d.data(), r.data(), t.data(), a, &p, small_temp, interp, nullptr));
+#else
+    check(hc_reset_internal_energy_host((int)t.size(), s.data(), d.data(), r.data(), t.data(), a, &p, small_temp, interp));
+#endif
+}

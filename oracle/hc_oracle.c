@@ -1106,3 +1106,65 @@ int hco_eos_box(const hco_rates* r, const hco_params* p, const hco_fab* state, c
     }
     return 0;
 }
+
+/* nyx_eos_given_RT (EOS/eos_hc.H:222-231): e from (T, Ne) */
+static double eos_e_given_T(double gamma_minus_1, double h_species, double T, double Ne) {
+    const double YHELIUM = (1.0 - h_species) / (4.0 * h_species);
+    const double mu = (1.0 + 4.0 * YHELIUM) / (1.0 + YHELIUM + Ne);
+    return T / (gamma_minus_1 * MP_OVER_KB * mu);
+}
+
+/* the cell loop of Nyx::compute_new_temp (DRV/Nyx.cpp:2473-2519) */
+int hco_compute_new_temp_box(const hco_rates* r, const hco_params* p, const hco_fab* state, const hco_fab* diag, const int lo[3], const int hi[3],
+                             double a, double small_temp, double large_temp, int max_temp_dt) {
+    for (int k = lo[2]; k <= hi[2]; ++k) for (int j = lo[1]; j <= hi[1]; ++j) for (int i = lo[0]; i <= hi[0]; ++i) {
+        const double rho = *at(state, i, j, k, DENS);
+        const double rhoInv = 1.0 / rho;
+        double eint;
+        if (*at(state, i, j, k, EINT) > 0.0) {
+            double sp[5];
+            eos_T_given_Re(r, p->gamma_minus_1, p->h_species, 1, 1, at(diag, i, j, k, TEMP), at(diag, i, j, k, NE), rho,
+                           *at(state, i, j, k, EINT) * (1.0 / rho), a, sp);
+            if (*at(diag, i, j, k, TEMP) >= large_temp && max_temp_dt == 1) {
+                *at(diag, i, j, k, TEMP) = large_temp;
+                eint = eos_e_given_T(p->gamma_minus_1, p->h_species, *at(diag, i, j, k, TEMP), *at(diag, i, j, k, NE));
+                const double ke = 0.5e0 * (*at(state, i, j, k, 1) * *at(state, i, j, k, 1) + *at(state, i, j, k, 2) * *at(state, i, j, k, 2) +
+                                           *at(state, i, j, k, 3) * *at(state, i, j, k, 3)) * rhoInv;
+                *at(state, i, j, k, EINT) = rho * eint;
+                *at(state, i, j, k, EDEN) = *at(state, i, j, k, EINT) + ke;
+            }
+        } else {
+            eint = eos_e_given_T(p->gamma_minus_1, p->h_species, small_temp, *at(diag, i, j, k, NE));
+            const double ke = 0.5e0 * (*at(state, i, j, k, 1) * *at(state, i, j, k, 1) + *at(state, i, j, k, 2) * *at(state, i, j, k, 2) +
+                                       *at(state, i, j, k, 3) * *at(state, i, j, k, 3)) * rhoInv;
+            *at(diag, i, j, k, TEMP) = small_temp;
+            *at(state, i, j, k, EINT) = rho * eint;
+            *at(state, i, j, k, EDEN) = *at(state, i, j, k, EINT) + ke;
+        }
+    }
+    return 0;
+}
+
+/* reset_internal_e (EOS/reset_internal_e.H:16-68) over a box: the cell loop of Nyx::reset_internal_energy (DRV/Nyx.cpp:2356-2385) */
+int hco_reset_internal_e_box(const hco_params* p, const hco_fab* u, const hco_fab* d, const hco_fab* rs, const int lo[3], const int hi[3],
+                             double small_temp, int interp) {
+    for (int k = lo[2]; k <= hi[2]; ++k) for (int j = lo[1]; j <= hi[1]; ++j) for (int i = lo[0]; i <= hi[0]; ++i) {
+        const double rhoInv = 1.0 / *at(u, i, j, k, DENS);
+        const double Up = *at(u, i, j, k, 1) * rhoInv, Vp = *at(u, i, j, k, 2) * rhoInv, Wp = *at(u, i, j, k, 3) * rhoInv;
+        const double ke = 0.5 * *at(u, i, j, k, DENS) * (Up * Up + Vp * Vp + Wp * Wp);
+        const double rho_eint = *at(u, i, j, k, EDEN) - ke;
+        if (rho_eint > 0.0 && rho_eint / *at(u, i, j, k, EDEN) > 1.0e-6 && interp == 0) {
+            *at(rs, i, j, k, 0) = rho_eint - *at(u, i, j, k, EINT);
+            *at(u, i, j, k, EINT) = rho_eint;
+        } else if (*at(u, i, j, k, EINT) > 0.0) {
+            *at(rs, i, j, k, 0) += 0.0;
+            *at(u, i, j, k, EDEN) = *at(u, i, j, k, EINT) + ke;
+        } else if (*at(u, i, j, k, EINT) <= 0.0) {
+            const double eint_new = eos_e_given_T(p->gamma_minus_1, p->h_species, small_temp, *at(d, i, j, k, NE));
+            *at(rs, i, j, k, 0) = *at(u, i, j, k, DENS) * eint_new - *at(u, i, j, k, EINT);
+            *at(u, i, j, k, EINT) = *at(u, i, j, k, DENS) * eint_new;
+            *at(u, i, j, k, EDEN) = *at(u, i, j, k, EINT) + ke;
+        }
+    }
+    return 0;
+}

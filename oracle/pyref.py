@@ -112,6 +112,20 @@ class Reference:
         return self.lib.nyxref_integrate_state_struct(len(b), bp, ngarr, ncd, _ptrs(s_old), _ptrs(s_new), _ptrs(d_old),
                                                       _ptrs(hydro_src), _ptrs(ir), _ptrs(reset_src), a, a_end, dt, sdc_iter)
 
+    def compute_new_temp(self, box, state, diag, a, small_temp, large_temp, max_temp_dt, ng_state=0, ng_diag=0):
+        """cell loop of Nyx::compute_new_temp over one box (restated around the reference's EOS functions, ref_driver.cpp)"""
+        b, bp = self._boxes([box])
+        self.lib.nyxref_compute_new_temp.argtypes = [C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int, _dp, _dp, C.c_double, C.c_double, C.c_double, C.c_int]
+        self.lib.nyxref_compute_new_temp(bp, ng_state, ng_diag, diag.shape[0], state.ctypes.data_as(_dp), diag.ctypes.data_as(_dp), a,
+                                         small_temp, large_temp, max_temp_dt)
+
+    def reset_internal_energy(self, box, state, diag, reset_src, a, small_temp, interp=0, ng_state=0, ng_diag=0, ng_reset=0):
+        """cell loop of Nyx::reset_internal_energy over one box: the reference's reset_internal_e.H"""
+        b, bp = self._boxes([box])
+        self.lib.nyxref_reset_internal_energy.argtypes = [C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, C.c_double, C.c_double, C.c_int]
+        self.lib.nyxref_reset_internal_energy(bp, ng_state, ng_diag, diag.shape[0], ng_reset, state.ctypes.data_as(_dp), diag.ctypes.data_as(_dp),
+                                              reset_src.ctypes.data_as(_dp), a, small_temp, interp)
+
     def ion_n(self, JH, JHe, U, nh, ne, gm1, hsp, z):
         out = np.zeros(4)
         self.lib.nyxref_ion_n(JH, JHe, U, nh, ne, gm1, hsp, z, out.ctypes.data_as(_dp))
@@ -232,6 +246,22 @@ class Port:
         self.lib.hco_integrate_state_struct(self.rp, C.byref(p), *[C.byref(f) for f in fabs], l, h, a, a_end, dt, sdc_iter,
                                             st.ctypes.data_as(C.c_void_p) if want_stats else None)
         return st
+
+    def compute_new_temp(self, state, diag, lo, hi, a, small_temp, large_temp, max_temp_dt, params=None):
+        p = params or self.params()
+        sf, df = fab_of(state, lo), fab_of(diag, lo)
+        l, h = self._box(lo, hi)
+        self.lib.hco_compute_new_temp_box.argtypes = [C.c_void_p, C.POINTER(HcoParams), C.POINTER(type(sf)), C.POINTER(type(sf)), type(l), type(l),
+                                                      C.c_double, C.c_double, C.c_double, C.c_int]
+        self.lib.hco_compute_new_temp_box(self.rp, C.byref(p), C.byref(sf), C.byref(df), l, h, a, small_temp, large_temp, max_temp_dt)
+
+    def reset_internal_energy(self, state, diag, reset_src, lo, hi, small_temp, interp=0, params=None):
+        p = params or self.params()
+        sf, df, rf = fab_of(state, lo), fab_of(diag, lo), fab_of(reset_src, lo)
+        l, h = self._box(lo, hi)
+        self.lib.hco_reset_internal_e_box.argtypes = [C.POINTER(HcoParams), C.POINTER(type(sf)), C.POINTER(type(sf)), C.POINTER(type(sf)), type(l), type(l),
+                                                      C.c_double, C.c_int]
+        self.lib.hco_reset_internal_e_box(C.byref(p), C.byref(sf), C.byref(df), C.byref(rf), l, h, small_temp, interp)
 
     def eos_box(self, state, diag, lo, hi, a, params=None):
         p = params or self.params()

@@ -185,3 +185,74 @@ void nyxref_interp_to_this_z(double z, double* out6) {
     interp_to_this_z(atomic_rates_glob, z, out6[0], out6[1], out6[2], out6[3], out6[4], out6[5]);
 }
 }
+
+// ---- the next rows of the hot-path table: Nyx::reset_internal_energy and Nyx::compute_new_temp.
+// Both live in Source/Driver/Nyx.cpp, which cannot be compiled without the whole application.  reset_internal_energy's cell
+// body is the reference header Source/EOS/reset_internal_e.H, called here exactly as Nyx.cpp:2377-2382 calls it.
+// compute_new_temp's cell body is a lambda inside Nyx.cpp:2473-2519: its branch structure is RESTATED below around the
+// reference's own nyx_eos_T_given_Re_device / nyx_eos_given_RT (eos_hc.H:204-231), statement by statement.
+#include <reset_internal_e.H>
+extern "C" {
+void nyxref_reset_internal_energy(const int* box, int ng_state, int ng_diag, int ncomp_diag, int ng_reset, double* state, double* diag,
+                                  double* reset_src, double a, double small_temp, int interp) {
+    BoxArray ba = make_ba(1, box);
+    MultiFab S, D, R;
+    double* sp[1] = {state}; double* dp[1] = {diag}; double* rp[1] = {reset_src};
+    S.defineAlias(ba, 6, ng_state, sp);
+    D.defineAlias(ba, ncomp_diag, ng_diag, dp);
+    R.defineAlias(ba, 1, ng_reset, rp);
+    const Real gamma_minus_1 = Nyx::gamma - 1.0;
+    for (MFIter mfi(S); mfi.isValid(); ++mfi) {
+        const Box& bx = mfi.validbox();
+        const auto fab = S.array(mfi);
+        const auto fab_diag = D.array(mfi);
+        const auto fab_reset = R.array(mfi);
+        for (int k = bx.smallEnd(2); k <= bx.bigEnd(2); ++k) for (int j = bx.smallEnd(1); j <= bx.bigEnd(1); ++j) for (int i = bx.smallEnd(0); i <= bx.bigEnd(0); ++i)
+            reset_internal_e(i, j, k, fab, fab_diag, fab_reset, atomic_rates_glob, a, gamma_minus_1, Nyx::h_species, small_temp, interp);
+    }
+}
+
+void nyxref_compute_new_temp(const int* box, int ng_state, int ng_diag, int ncomp_diag, double* state, double* diag, double a,
+                             double local_small_temp, double local_large_temp, int local_max_temp_dt) {
+    BoxArray ba = make_ba(1, box);
+    MultiFab S, D;
+    double* sp[1] = {state}; double* dp[1] = {diag};
+    S.defineAlias(ba, 6, ng_state, sp);
+    D.defineAlias(ba, ncomp_diag, ng_diag, dp);
+    const Real h_species_in = Nyx::h_species, gamma_minus_1_in = Nyx::gamma - 1.0;
+    AtomicRates* atomic_rates = atomic_rates_glob;
+    for (MFIter mfi(S); mfi.isValid(); ++mfi) {
+        const Box& bx = mfi.validbox();
+        const auto state_fab = S.array(mfi);
+        const auto diag_eos_fab = D.array(mfi);
+        for (int k = bx.smallEnd(2); k <= bx.bigEnd(2); ++k) for (int j = bx.smallEnd(1); j <= bx.bigEnd(1); ++j) for (int i = bx.smallEnd(0); i <= bx.bigEnd(0); ++i) {
+            Real rhoInv = 1.0 / state_fab(i,j,k,Density_comp);
+            Real eint = state_fab(i,j,k,Eint_comp) * rhoInv;
+            if (state_fab(i,j,k,Eint_comp) > 0.0) {
+                nyx_eos_T_given_Re_device(atomic_rates, gamma_minus_1_in, h_species_in, 1, 1,
+                                          &diag_eos_fab(i,j,k,Temp_comp), &diag_eos_fab(i,j,k,Ne_comp),
+                                          state_fab(i,j,k,Density_comp), state_fab(i,j,k,Eint_comp) * (1.0 / state_fab(i,j,k,Density_comp)), a);
+                if (diag_eos_fab(i,j,k,Temp_comp) >= local_large_temp && local_max_temp_dt == 1) {
+                    diag_eos_fab(i,j,k,Temp_comp) = local_large_temp;
+                    Real dummy_pres = 0.0;
+                    nyx_eos_given_RT(atomic_rates, gamma_minus_1_in, h_species_in, &eint, &dummy_pres,
+                                     state_fab(i,j,k,Density_comp), diag_eos_fab(i,j,k,Temp_comp), diag_eos_fab(i,j,k,Ne_comp), a);
+                    Real ke = 0.5e0 * (state_fab(i,j,k,Xmom_comp) * state_fab(i,j,k,Xmom_comp) + state_fab(i,j,k,Ymom_comp) * state_fab(i,j,k,Ymom_comp) +
+                                       state_fab(i,j,k,Zmom_comp) * state_fab(i,j,k,Zmom_comp)) * rhoInv;
+                    state_fab(i,j,k,Eint_comp) = state_fab(i,j,k,Density_comp) * eint;
+                    state_fab(i,j,k,Eden_comp) = state_fab(i,j,k,Eint_comp) + ke;
+                }
+            } else {
+                Real dummy_pres = 0.0;
+                nyx_eos_given_RT(atomic_rates, gamma_minus_1_in, h_species_in, &eint, &dummy_pres,
+                                 state_fab(i,j,k,Density_comp), local_small_temp, diag_eos_fab(i,j,k,Ne_comp), a);
+                Real ke = 0.5e0 * (state_fab(i,j,k,Xmom_comp) * state_fab(i,j,k,Xmom_comp) + state_fab(i,j,k,Ymom_comp) * state_fab(i,j,k,Ymom_comp) +
+                                   state_fab(i,j,k,Zmom_comp) * state_fab(i,j,k,Zmom_comp)) * rhoInv;
+                diag_eos_fab(i,j,k,Temp_comp) = local_small_temp;
+                state_fab(i,j,k,Eint_comp) = state_fab(i,j,k,Density_comp) * eint;
+                state_fab(i,j,k,Eden_comp) = state_fab(i,j,k,Eint_comp) + ke;
+            }
+        }
+    }
+}
+}

@@ -31,6 +31,8 @@ long int Nyx::old_max_sundials_steps = 3;
 long int Nyx::new_max_sundials_steps = 3;
 
 extern "C" const HcStats* nyx_hc_last_stats();
+void nyx_hc_compute_new_temp(MultiFab& S_new, MultiFab& D_new, Real a, Real small_temp, Real large_temp, int max_temp_dt);
+void nyx_hc_reset_internal_energy(MultiFab& S_new, MultiFab& D_new, MultiFab& reset_e_src, Real a, Real small_temp, int interp);
 extern "C" int nyx_hc_setup(const char* treecool_path, double mean_rhob);
 
 extern "C" {
@@ -88,6 +90,27 @@ int nyxref_integrate_state_struct(int nboxes, const int* boxes, const int* ng, i
     R.defineAlias(ba, 1, ng[5], reset_src);
     Nyx nyx;
     return nyx.integrate_state_struct(S_old, S_new, D_old, H, IR, R, a, a_end, dt, sdc_iter);
+}
+
+void nyxref_compute_new_temp(const int* box, int ng_state, int ng_diag, int ncomp_diag, double* state, double* diag, double a,
+                             double small_temp, double large_temp, int max_temp_dt) {
+    BoxArray ba = make_ba(1, box);
+    MultiFab S, D;
+    double* sp[1] = {state}; double* dp[1] = {diag};
+    S.defineAlias(ba, 6, ng_state, sp);
+    D.defineAlias(ba, ncomp_diag, ng_diag, dp);
+    nyx_hc_compute_new_temp(S, D, a, small_temp, large_temp, max_temp_dt);
+}
+
+void nyxref_reset_internal_energy(const int* box, int ng_state, int ng_diag, int ncomp_diag, int ng_reset, double* state, double* diag,
+                                  double* reset_src, double a, double small_temp, int interp) {
+    BoxArray ba = make_ba(1, box);
+    MultiFab S, D, R;
+    double* sp[1] = {state}; double* dp[1] = {diag}; double* rp[1] = {reset_src};
+    S.defineAlias(ba, 6, ng_state, sp);
+    D.defineAlias(ba, ncomp_diag, ng_diag, dp);
+    R.defineAlias(ba, 1, ng_reset, rp);
+    nyx_hc_reset_internal_energy(S, D, R, a, small_temp, interp);
 }
 
 }  // extern "C"

@@ -118,3 +118,25 @@ def test_dropin_use_typical_steps_updates_max_steps(dropin):
     finally:
         dropin.set("nyx.use_typical_steps", 0)
         dropin.set("nyx.new_max_sundials_steps", 3)
+
+
+@pytest.mark.gpu
+def test_dropin_eos_rows_vs_reference(dropin, reference):
+    """SURVEY 8f rank 1 through the C++ drop-in (host FABs with ghost cells, staged by the *_host entry points): reset_internal_energy
+    bit for bit, compute_new_temp to the tight EOS tolerance."""
+    n, ng, z = 12, 2, 3.0
+    a = 1.0 / (1.0 + z)
+    m = n + 2 * ng
+    box = (0, 0, 0, n - 1, n - 1, n - 1)
+    state, diag, rs = util.eos_rows_inputs(m, 601, z)
+    s1, d1, r1 = state.copy(), diag.copy(), rs.copy()
+    reference.reset_internal_energy(box, s1, d1, r1, a, 1.0e-2, 0, ng, ng, ng)
+    dropin.reset_internal_energy(box, state, diag, rs, a, 1.0e-2, 0, ng, ng, ng)
+    assert np.array_equal(s1, state) and np.array_equal(r1, rs) and np.array_equal(d1, diag)
+    reference.compute_new_temp(box, s1, d1, a, 1.0e-2, 3.0e6, 1, ng, ng)
+    dropin.compute_new_temp(box, state, diag, a, 1.0e-2, 3.0e6, 1, ng, ng)
+    ok = d1[0] > 1.0e2
+    assert np.abs(diag[0] / d1[0] - 1.0)[ok].max() < 1e-5 and np.abs(diag[1] - d1[1])[ok].max() < 1e-5
+    assert np.all(np.abs(state[5] - s1[5]) <= 1e-9 * np.abs(s1[5])) and np.all(np.abs(state[4] - s1[4]) <= 1e-9 * np.abs(s1[4]))
+    # (reset_internal_energy has just repaired the cells with rho e <= 0, so only the clipping branch is left to see here)
+    assert (diag[0] == 1.0e-2).sum() == (d1[0] == 1.0e-2).sum() and (diag[0] == 3.0e6).sum() == (d1[0] == 3.0e6).sum() > 0

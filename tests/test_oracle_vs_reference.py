@@ -98,3 +98,32 @@ def test_struct_percell_mode_bitwise(reference, port, z, seed, src, flash):
     for k in ("s_old", "s_new", "diag", "ir"):
         assert np.array_equal(d[k], r[k]), k
     assert np.array_equal(reference.stats(), pst[:, :8])
+
+
+@pytest.mark.parametrize("interp", [0, 1])
+def test_reset_internal_energy_bitwise(reference, port, interp):
+    """the port's reset_internal_e loop against the reference header Source/EOS/reset_internal_e.H."""
+    n = 12
+    state, diag, rs = util.eos_rows_inputs(n, 401)
+    lo, hi = (0, 0, 0), (n - 1, n - 1, n - 1)
+    s1, d1, r1 = state.copy(), diag.copy(), rs.copy()
+    reference.reset_internal_energy(lo + hi, s1, d1, r1, 0.25, 1.0e-2, interp)
+    port.reset_internal_energy(state, diag, rs, lo, hi, 1.0e-2, interp)
+    assert np.array_equal(s1, state) and np.array_equal(d1, diag) and np.array_equal(r1, rs)
+    assert not np.array_equal(state, util.eos_rows_inputs(n, 401)[0])        # something was reset
+
+
+@pytest.mark.parametrize("max_temp_dt,large_temp", [(0, 1.0e9), (1, 3.0e6)])
+def test_compute_new_temp_bitwise(reference, port, max_temp_dt, large_temp):
+    """the port's compute_new_temp loop against the reference's EOS functions driven as Nyx.cpp:2473-2519 drives them."""
+    n, z = 12, 3.0
+    a = 1.0 / (1.0 + z)
+    state, diag, _ = util.eos_rows_inputs(n, 402, z)
+    lo, hi = (0, 0, 0), (n - 1, n - 1, n - 1)
+    s1, d1 = state.copy(), diag.copy()
+    reference.compute_new_temp(lo + hi, s1, d1, a, 1.0e-2, large_temp, max_temp_dt)
+    port.compute_new_temp(state, diag, lo, hi, a, 1.0e-2, large_temp, max_temp_dt)
+    assert np.array_equal(s1, state) and np.array_equal(d1, diag)
+    assert (diag[0] == 1.0e-2).any()                                           # the rho e <= 0 branch ran
+    if max_temp_dt:
+        assert (diag[0] == large_temp).any()                                   # and the clipping branch

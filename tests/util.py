@@ -31,6 +31,27 @@ def sdc_inputs(z, n, seed, src_scale=0.0):
     return dict(a=a, a_end=a_end, dt=dt, s_old=s_old, s_new=s_new, diag=diag, hydro_src=hs, reset_src=rs, ir=ir)
 
 
+def eos_rows_inputs(n, seed, z=3.0):
+    """A box for Nyx::compute_new_temp / reset_internal_energy: the synthetic LyA field plus momenta, a total energy that is (in
+    parts of the box) inconsistent with rho e, cells with rho e <= 0, very hot cells (large_temp clipping) and stale diag(Ne)."""
+    rng = np.random.default_rng(seed)
+    state, diag = synth.make_fab((n, n, n), seed=seed, z=z)
+    rho = state[0]
+    for c in (1, 2, 3):
+        state[c] = rho * 300.0 * rng.standard_normal((n, n, n))          # momenta: ~300 km/s
+    ke = 0.5 * (state[1] ** 2 + state[2] ** 2 + state[3] ** 2) / rho
+    state[4] = state[5] + ke
+    u = rng.random((n, n, n))
+    state[4] = np.where(u < 0.10, state[5] * 0.5 + ke, state[4])          # rho E inconsistent with rho e
+    state[4] = np.where((u >= 0.10) & (u < 0.15), ke * (1.0 + 1e-8), state[4])   # (e from E) below 1e-6 of E
+    state[5] = np.where((u >= 0.15) & (u < 0.20), -np.abs(state[5]), state[5])   # negative rho e
+    state[5] = np.where((u >= 0.20) & (u < 0.22), 0.0, state[5])
+    state[5] = np.where((u >= 0.22) & (u < 0.25), state[5] * 1e3, state[5])      # very hot
+    diag[1] = rng.uniform(0.0, 1.2, (n, n, n))                            # the cell's current ne
+    reset_src = rng.standard_normal((1, n, n, n)) * 1e-3
+    return state, diag, reset_src
+
+
 FLASH_CASES = {
     "none": {},
     "hi_now": dict(zhi_flash=5.98, T_zhi=2e4, zheii_flash=3.0, T_zheii=1.5e4),     # with z = 5.99: H flash inside the step
