@@ -146,6 +146,29 @@ __device__ __forceinline__ int find_tile_by_chunk(const TileDesc* tiles, int nti
     return lo;
 }
 
+// the tile that holds global cell `id` (tiles are concatenated in `offset` order)
+__device__ __forceinline__ int find_tile_by_cell(const TileDesc* tiles, int ntiles, long long id) {
+    int lo = 0, hi = ntiles - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (tiles[mid].offset <= id) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+// grid-stride loops visit the cells in increasing order: walk forward from the tile of the previous cell (binary search the first time)
+__device__ __forceinline__ int next_tile(const KernelArgs& a, int t, long long id) {
+    if (t < 0) return find_tile_by_cell(a.tiles, a.ntiles, id);
+    while (t + 1 < a.ntiles && a.tiles[t + 1].offset <= id) ++t;
+    return t;
+}
+__device__ __forceinline__ void cell_of(const TileDesc& t, long long id, int& i, int& j, int& k) {
+    const unsigned local = (unsigned)(id - t.offset);
+    const unsigned row = local / (unsigned)t.nx, kk = row / (unsigned)t.ny;
+    i = t.lo[0] + (int)(local - row * (unsigned)t.nx);
+    j = t.lo[1] + (int)(row - kk * (unsigned)t.ny);
+    k = t.lo[2] + (int)kk;
+}
+
 // stage the ionization tables into shared memory (16-byte vector copies)
 __device__ __forceinline__ void stage_tables(const KernelArgs& a, double* s_ionx, double* s_iony) {
     const double2* src = reinterpret_cast<const double2*>(a.ionx);
@@ -346,7 +369,7 @@ __global__ void __launch_bounds__(THREADS, 1) hc_integrate_kernel(const __grid_c
     flush_totals(tot, s_stats, a.dstats);
 }
 
-// EOS kernel: one thread per cell, grid-stride over the cells of one tile; ionization tables staged in shared memory.
+// EOS kernel: one thread per cell, grid-stride over the cells of all tiles; ionization tables staged in shared memory.
 //   eos_mode 0: diag(Temp, Ne) = nyx_eos_T_given_Re(rho, rho_e / rho)                       (eos_hc.H:204-220)
 //   eos_mode 1: the cell body of Nyx::compute_new_temp (Source/Driver/Nyx.cpp:2473-2519): e = rho_e * (1 / rho); cells at or above
 //               large_temp are clipped (max_temp_dt), cells with rho_e <= 0 are reset to small_temp; both rewrite (rho e, rho E).
@@ -361,15 +384,14 @@ __global__ void __launch_bounds__(THREADS, 1) hc_eos_kernel(const __grid_constan
     const Tables tb{s_ionx, s_iony, a.cool, a.logtab};
     const Consts& c = a.k;
     unsigned long long iters = 0, cells = 0, n_eos = 0, n_small = 0, n_large = 0;
-    const TileDesc& t = a.tiles[0];
-    const long long plane = (long long)t.nx * t.ny;
-    const HcFab& S = t.f[F_STATE];
-    const HcFab& D = t.f[F_DIAG];
+    int ti = -1;
     for (long long id = (long long)blockIdx.x * THREADS + threadIdx.x; id < a.ncells; id += (long long)gridDim.x * THREADS) {
-        const int kk = (int)(id / plane);
-        const int rem = (int)(id - (long long)kk * plane);
-        const int jj = rem / t.nx;
-        const int i = t.lo[0] + (rem - jj * t.nx), j = t.lo[1] + jj, k = t.lo[2] + kk;
+        ti = next_tile(a, ti, id);
+        const TileDesc& t = a.tiles[ti];
+        const HcFab& S = t.f[F_STATE];
+        const HcFab& D = t.f[F_DIAG];
+        int i, j, k;
+        cell_of(t, id, i, j, k);
         const long long so = fab_off(S, i, j, k), dof = fab_off(D, i, j, k);
         const double R = S.p[so + DENS * S.nstride];
         const double rhoe = S.p[so + EINT * S.nstride];
@@ -420,42 +442,63 @@ __global__ void __launch_bounds__(THREADS, 1) hc_eos_kernel(const __grid_constan
     if (threadIdx.x < S_COUNT) atomicAdd(&a.dstats[threadIdx.x], s_stats[threadIdx.x]);
 }
 
-// reset_internal_e (Source/EOS/reset_internal_e.H:16-68) over one tile: synchronises (rho e) and (rho E), records the change of
+// reset_internal_e (Source/EOS/reset_internal_e.H:16-68) over all tiles: synchronises (rho e) and (rho E), records the change of
 // (rho e) in the reset source.  Pure streaming: 8 doubles read, up to 3 written per cell.
 __global__ void __launch_bounds__(256) hc_reset_e_kernel(const __grid_constant__ KernelArgs a) {
     const Consts& c = a.k;
-    const TileDesc& t = a.tiles[0];
-    const long long plane = (long long)t.nx * t.ny;
-    const HcFab& U = t.f[F_STATE];
-    const HcFab& D = t.f[F_DIAG];
-    const HcFab& Rs = t.f[2];
-    for (long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x; id < a.ncells; id += (long long)gridDim.x * blockDim.x) {
-        const int kk = (int)(id / plane);
-        const int rem = (int)(id - (long long)kk * plane);
-        const int jj = rem / t.nx;
-        const int i = t.lo[0] + (rem - jj * t.nx), j = t.lo[1] + jj, k = t.lo[2] + kk;
-        const long long so = fab_off(U, i, j, k);
-        double* pr = Rs.p + fab_off(Rs, i, j, k);
-        const double rho = U.p[so + DENS * U.nstride];
-        const double rhoInv = 1.0 / rho;
-        const double Up = U.p[so + 1 * U.nstride] * rhoInv, Vp = U.p[so + 2 * U.nstride] * rhoInv, Wp = U.p[so + 3 * U.nstride] * rhoInv;
-        const double ke = 0.5 * rho * (Up * Up + Vp * Vp + Wp * Wp);
-        const double eden = U.p[so + EDEN * U.nstride], eint = U.p[so + EINT * U.nstride];
-        const double rho_eint = eden - ke;
-        if (rho_eint > 0.0 && rho_eint / eden > 1.0e-6 && a.interp == 0) {
-            *pr = rho_eint - eint;
-            U.p[so + EINT * U.nstride] = rho_eint;
-        } else if (eint > 0.0) {
-            *pr += 0.0;
-            U.p[so + EDEN * U.nstride] = eint + ke;
-        } else if (eint <= 0.0) {
-            const double ne = D.p[fab_off(D, i, j, k) + NE * D.nstride];
-            const double mu = c.c_mu_num / (c.c_mu_den + ne);
-            const double eint_new = a.small_temp / (c.gm1 * mp_over_kb * mu);
-            const double re = rho * eint_new;
-            *pr = re - eint;
-            U.p[so + EINT * U.nstride] = re;
-            U.p[so + EDEN * U.nstride] = re + ke;
+    constexpr int U4 = 4;   // cells per thread and pass: all loads of a pass are issued before the first store
+    int t0 = -1;
+    for (long long base = (long long)blockIdx.x * (256 * U4); base < a.ncells; base += (long long)gridDim.x * (256 * U4)) {
+        t0 = next_tile(a, t0, base);
+        double v[U4][8];
+        double* pu[U4]; double* pr[U4];
+        long long ns[U4];
+        bool on[U4];
+#pragma unroll
+        for (int u = 0; u < U4; ++u) {
+            const long long id = base + u * 256 + threadIdx.x;
+            on[u] = id < a.ncells;
+            pu[u] = nullptr; pr[u] = nullptr; ns[u] = 0;
+            if (on[u]) {
+                int ti = t0;
+                while (ti + 1 < a.ntiles && a.tiles[ti + 1].offset <= id) ++ti;
+                const TileDesc& t = a.tiles[ti];
+                const HcFab& Uf = t.f[F_STATE];
+                const HcFab& D = t.f[F_DIAG];
+                const HcFab& Rs = t.f[2];
+                int i, j, k;
+                cell_of(t, id, i, j, k);
+                pu[u] = Uf.p + fab_off(Uf, i, j, k); ns[u] = Uf.nstride;
+                pr[u] = Rs.p + fab_off(Rs, i, j, k);
+#pragma unroll
+                for (int n = 0; n < 6; ++n) v[u][n] = pu[u][n * ns[u]];
+                v[u][6] = D.p[fab_off(D, i, j, k) + NE * D.nstride];
+                v[u][7] = *pr[u];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U4; ++u) {
+            if (!on[u]) continue;
+            const double rho = v[u][DENS];
+            const double rhoInv = 1.0 / rho;
+            const double Up = v[u][1] * rhoInv, Vp = v[u][2] * rhoInv, Wp = v[u][3] * rhoInv;
+            const double ke = 0.5 * rho * (Up * Up + Vp * Vp + Wp * Wp);
+            const double eden = v[u][EDEN], eint = v[u][EINT];
+            const double rho_eint = eden - ke;
+            if (rho_eint > 0.0 && rho_eint / eden > 1.0e-6 && a.interp == 0) {
+                *pr[u] = rho_eint - eint;
+                pu[u][EINT * ns[u]] = rho_eint;
+            } else if (eint > 0.0) {
+                *pr[u] = v[u][7] + 0.0;
+                pu[u][EDEN * ns[u]] = eint + ke;
+            } else if (eint <= 0.0) {
+                const double mu = c.c_mu_num / (c.c_mu_den + v[u][6]);
+                const double eint_new = a.small_temp / (c.gm1 * mp_over_kb * mu);
+                const double re = rho * eint_new;
+                *pr[u] = re - eint;
+                pu[u][EINT * ns[u]] = re;
+                pu[u][EDEN * ns[u]] = re + ke;
+            }
         }
     }
 }
@@ -553,7 +596,7 @@ struct EosOpts {
     int mode = 0, max_temp_dt = 0, interp = 0;
     double small_temp = 0.0, large_temp = 0.0;
 };
-constexpr int PATH_RESET_E = 3;   // hc_reset_e_kernel (PATH_EOS = 2: hc_eos_kernel); both take ONE tile per launch
+constexpr int PATH_RESET_E = 3;   // hc_reset_e_kernel (PATH_EOS = 2: hc_eos_kernel)
 
 int launch(int path, int ntiles, const HcFab* const* fabs, int nf, const HcBox* tiles, const Consts& k, HcStats* stats,
            HcCellStat* cell_stats, cudaStream_t stream, unsigned long long* ext_dstats = nullptr, const EosOpts* eos = nullptr) {
@@ -616,7 +659,7 @@ int launch(int path, int ntiles, const HcFab* const* fabs, int nf, const HcBox* 
     } else {
 #endif
         if (path == PATH_RESET_E) {
-            const int g = (int)std::min<long long>((ncells + 255) / 256, (long long)dt.sm_count * 8);
+            const int g = (int)std::min<long long>((ncells + 1023) / 1024, (long long)dt.sm_count * 8);
             hc_reset_e_kernel<<<g, 256, 0, stream>>>(a);
         } else {
             if (int rc = set_smem_attr(hc_eos_kernel, dt, 2, SMEM_EOS)) return rc;
@@ -714,15 +757,7 @@ int run_host(int path, int ntiles, std::vector<HostSlot>& slots, const HcBox* ti
         CUDA_TRY(cudaStreamWaitEvent(hp->comp, e_in, 0));
         std::vector<const HcFab*> fabs(nf);
         for (int s = 0; s < nf; ++s) fabs[s] = dfab[s].data();
-        if (path == PATH_EOS || path == PATH_RESET_E) {   // one tile per launch
-            for (int i = 0; i < n && rc == HC_OK; ++i) {
-                std::vector<const HcFab*> one(nf);
-                for (int s = 0; s < nf; ++s) one[s] = dfab[s].data() + i;
-                rc = launch(path, 1, one.data(), nf, tiles + t0 + i, k, nullptr, nullptr, hp->comp, dstats, eos);
-            }
-        } else {
-            rc = launch(path, n, fabs.data(), nf, tiles + t0, k, nullptr, nullptr, hp->comp, dstats);
-        }
+        rc = launch(path, n, fabs.data(), nf, tiles + t0, k, nullptr, nullptr, hp->comp, dstats, eos);
         if (rc != HC_OK) break;
         CUDA_TRY(cudaEventRecord(e_k, hp->comp));
         CUDA_TRY(cudaStreamWaitEvent(hp->d2h, e_k, 0));
@@ -836,25 +871,9 @@ int hc_eos_T_given_Re(const HcFab* state, const HcFab* diag, HcBox tile, double 
 }
 
 namespace {
-// the one-tile-per-launch kernels over a list of tiles: statistics accumulate in one device buffer
-int launch_each(int path, int ntiles, const HcFab* const* fabs, int nf, const HcBox* tiles, const Consts& k, const EosOpts& eos, HcStats* stats,
-                cudaStream_t stream) {
-    if (stats) std::memset(stats, 0, sizeof *stats);
-    unsigned long long* dstats = nullptr;
-    CUDA_TRY(cudaMallocAsync((void**)&dstats, 128, stream));
-    CUDA_TRY(cudaMemsetAsync(dstats, 0, 128, stream));
-    int rc = HC_OK;
-    for (int t = 0; t < ntiles && rc == HC_OK; ++t) {
-        const HcFab* one[6];
-        for (int s = 0; s < nf; ++s) one[s] = fabs[s] + t;
-        rc = launch(path, 1, one, nf, tiles + t, k, nullptr, nullptr, stream, dstats, &eos);
-    }
-    if (rc == HC_OK && stats) {
-        CUDA_TRY(cudaMemcpyAsync(stats, dstats, sizeof(HcStats), cudaMemcpyDeviceToHost, stream));
-        CUDA_TRY(cudaStreamSynchronize(stream));
-    }
-    CUDA_TRY(cudaFreeAsync(dstats, stream));
-    return rc;
+int launch_eos(int path, int ntiles, const HcFab* const* fabs, int nf, const HcBox* tiles, const Consts& k, const EosOpts& eos, HcStats* stats,
+               cudaStream_t stream) {
+    return launch(path, ntiles, fabs, nf, tiles, k, stats, nullptr, stream, nullptr, &eos);
 }
 }  // namespace
 
@@ -865,7 +884,7 @@ int hc_compute_new_temp_batch(int ntiles, const HcFab* state, const HcFab* diag,
     const Consts k = make_consts_eos(g_rates.data(), *prm, a);
     EosOpts eos; eos.mode = 1; eos.small_temp = small_temp; eos.large_temp = large_temp; eos.max_temp_dt = max_temp_dt;
     const HcFab* fabs[2] = {state, diag};
-    return launch_each(PATH_EOS, ntiles, fabs, 2, tiles, k, eos, stats, (cudaStream_t)stream);
+    return launch_eos(PATH_EOS, ntiles, fabs, 2, tiles, k, eos, stats, (cudaStream_t)stream);
 }
 
 int hc_reset_internal_energy_batch(int ntiles, const HcFab* state, const HcFab* diag, const HcFab* reset_src, const HcBox* tiles, double a,
@@ -875,7 +894,7 @@ int hc_reset_internal_energy_batch(int ntiles, const HcFab* state, const HcFab* 
     const Consts k = make_consts_eos(g_rates.data(), *prm, a);
     EosOpts eos; eos.small_temp = small_temp; eos.interp = interp;
     const HcFab* fabs[3] = {state, diag, reset_src};
-    return launch_each(PATH_RESET_E, ntiles, fabs, 3, tiles, k, eos, nullptr, (cudaStream_t)stream);
+    return launch_eos(PATH_RESET_E, ntiles, fabs, 3, tiles, k, eos, nullptr, (cudaStream_t)stream);
 }
 
 int hc_integrate_vec_host(int ntiles, const HcFab* state, const HcFab* diag, const HcBox* tiles, double a, double dt,
