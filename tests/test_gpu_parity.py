@@ -324,3 +324,66 @@ def test_reset_internal_energy_matches_oracle_bitwise(hc_lib, port, interp):
                                                   C.c_double, C.c_int]
     port.lib.hco_reset_internal_e_box(C.byref(p), C.byref(sf), C.byref(df), C.byref(rf), l, h, 1.0e-2, interp)
     assert np.array_equal(s_dev.cpu().numpy(), state) and np.array_equal(r_dev.cpu().numpy(), rs) and np.array_equal(d_dev.cpu().numpy(), diag)
+
+
+@pytest.mark.parametrize("n,z,path", [(128, 3.0, "vec"), (256, 2.0, "vec"), (128, 6.0, "struct")])
+def test_full_size_properties(hc_lib, n, z, path):
+    """BASELINE.json configs 2-5 at sizes the oracle cannot follow, through size-independent properties of the path:
+    (a) determinism: two runs give bit-identical FABs and counters, whatever order the work queue hands the cells out in;
+    (b) decomposition independence: every cell is integrated on its own, so the same field as ONE box, as 8 boxes or as 64 boxes
+        (each box its own FAB) gives bit-identical cell values and identical summed counters -- this is what box sharding over
+        GPUs relies on (SURVEY 8e);
+    (c) counters: all cells integrated, none failed, none floored, max_nst bounded, and the statistics add up over boxes."""
+    torch = _torch()
+    a, dt = 1.0 / (1.0 + z), synth.step_dt(z)
+    state, diag = synth.make_fab((n, n, n), seed=77, z=z)
+    kw = dict(zhi_flash=6.0, T_zhi=2e4, zheii_flash=3.0, T_zheii=1.5e4) if path == "struct" else {}   # config 5: flash reionization at z = 6
+    prm = hc_lib.default_params(**kw)
+
+    def run(nsplit):
+        m = n // nsplit
+        keep, fabs, tiles = [], {k: [] for k in ("s", "d", "sn", "hs", "rs", "ir")}, []
+        for kb in range(nsplit):
+            for jb in range(nsplit):
+                for ib in range(nsplit):
+                    sl = (slice(None), slice(kb * m, (kb + 1) * m), slice(jb * m, (jb + 1) * m), slice(ib * m, (ib + 1) * m))
+                    lo = (ib * m, jb * m, kb * m)
+                    s = torch.from_numpy(np.ascontiguousarray(state[sl])).cuda()
+                    d = torch.from_numpy(np.ascontiguousarray(diag[sl])).cuda()
+                    ent = {"s": s, "d": d}
+                    if path == "struct":
+                        ent.update(sn=s.clone(), hs=torch.zeros_like(s), rs=torch.zeros((1, m, m, m), dtype=torch.float64, device="cuda"),
+                                   ir=torch.zeros((1, m, m, m), dtype=torch.float64, device="cuda"))
+                    keep.append(ent)
+                    for k2, v in ent.items():
+                        fabs[k2].append(capi.fab_of_torch(v, lo))
+                    tiles.append(capi.make_box(lo, tuple(x + m - 1 for x in lo)))
+        if path == "vec":
+            st = hc_lib.integrate_vec_batch(fabs["s"], fabs["d"], tiles, a, 0.5 * dt, params=prm)
+        else:
+            st = hc_lib.integrate_struct_batch(fabs["s"], fabs["d"], fabs["sn"], fabs["hs"], fabs["rs"], fabs["ir"], tiles, a, synth.a_after(z, dt), dt, 0, params=prm)
+        torch.cuda.synchronize()
+        out_s = np.empty_like(state); out_d = np.empty_like(diag)
+        b = 0
+        for kb in range(nsplit):
+            for jb in range(nsplit):
+                for ib in range(nsplit):
+                    sl = (slice(None), slice(kb * m, (kb + 1) * m), slice(jb * m, (jb + 1) * m), slice(ib * m, (ib + 1) * m))
+                    out_s[sl] = keep[b]["sn" if path == "struct" else "s"].cpu().numpy()
+                    out_d[sl] = keep[b]["d"].cpu().numpy()
+                    b += 1
+        return out_s, out_d, st.as_dict()
+
+    s1, d1, st1 = run(1)
+    s1b, d1b, st1b = run(1)
+    assert np.array_equal(s1, s1b) and np.array_equal(d1, d1b) and st1 == st1b                     # (a)
+    for nsplit in (2, 4):
+        s2, d2, st2 = run(nsplit)
+        assert np.array_equal(s1, s2) and np.array_equal(d1, d2), f"{nsplit}^3 boxes differ from one box"   # (b)
+        assert st2 == st1
+    assert st1["n_cells"] == n ** 3 and st1["n_failed"] == 0 and st1["n_floor"] == 0                # (c)
+    assert 3 <= st1["max_nst"] <= 200 and st1["sum_nst"] >= 3 * n ** 3
+    assert st1["sum_nfe"] + st1["sum_nfe_ls"] >= st1["sum_nni"] and st1["sum_attempts"] >= st1["sum_nst"]
+    assert np.isfinite(s1).all() and np.isfinite(d1).all() and (d1[0] > 0).all() and (d1[1] >= 0).all() and (d1[1] <= 1.0 + 2.0 * 0.0789474 + 1e-9).all()
+    for comp in (0, 1, 2, 3):
+        assert np.array_equal(s1[comp], state[comp])
