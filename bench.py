@@ -23,6 +23,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+# The contract is ONE JSON line on stdout.  Libraries write banners to file descriptor 1 (NCCL prints "NCCL version ..." there when
+# NCCL_DEBUG is set): keep a private handle on the real stdout for the result line and point fd 1 at stderr for everything else.
+_RESULT_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
 METRIC = "heatcool_cell_updates_per_s"
 UNIT = "cell-updates/s"
 TREECOOL = os.path.join(ROOT, "tests", "golden", "TREECOOL_middle")   # the reference's Exec/LyA/TREECOOL_middle (data file)
@@ -191,7 +196,7 @@ def run_reference_arm(args):
             "config": {"workload": workload_name(args), "note": "reference CPU/OpenMP implementation (oracle/_ref) on a bounded sample of the workload's boxes"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": info["cores"], "kind": info["kind"], "sample": info["sample"]},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_RESULT_OUT, flush=True)
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -403,7 +408,7 @@ def main():
                            "parallelism": "boxes sharded over %d GPU(s), no data-path collective, one scalar all-reduce of diagnostics" % world},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps, "roofline": roofline, "cpu_baseline": cpu,
                 "stats": gstats, "ms_steps": ms_steps, "wall_s_timed_loop": wall, "gen_s": t_gen}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_RESULT_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
