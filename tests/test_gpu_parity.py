@@ -387,3 +387,94 @@ def test_full_size_properties(hc_lib, n, z, path):
     assert np.isfinite(s1).all() and np.isfinite(d1).all() and (d1[0] > 0).all() and (d1[1] >= 0).all() and (d1[1] <= 1.0 + 2.0 * 0.0789474 + 1e-9).all()
     for comp in (0, 1, 2, 3):
         assert np.array_equal(s1[comp], state[comp])
+
+
+def test_ragged_and_empty_batches(hc_lib, port):
+    """Edge cases of the batch interface: no tiles at all, an empty tile among the tiles (hi < lo: an empty MFIter tile), boxes of
+    very different shapes in one launch (1 cell; a thin slab; rows longer than one work-queue chunk of 256 cells), and the
+    per-cell statistics buffer laid out tile after tile."""
+    torch = _torch()
+    z = 3.0
+    a, dt = 1.0 / (1.0 + z), 0.5 * synth.step_dt(z)
+    st = hc_lib.integrate_vec_batch([], [], [], a, dt)
+    assert st.n_cells == 0 and st.sum_nst == 0
+    shapes = [(1, 1, 1), (5, 7, 3), (300, 2, 2), (33, 2, 9)]
+    keep, fs, fd, tiles, refs = [], [], [], [], []
+    for b, shp in enumerate(shapes):
+        state, diag = synth.make_fab(shp, seed=80 + b, z=z)
+        lo = (3 * b, -b, 7)
+        hi = tuple(l + s - 1 for l, s in zip(lo, shp))
+        s_dev, d_dev = torch.from_numpy(state).cuda(), torch.from_numpy(diag).cuda()
+        keep += [s_dev, d_dev]
+        fs.append(capi.fab_of_torch(s_dev, lo)); fd.append(capi.fab_of_torch(d_dev, lo)); tiles.append(capi.make_box(lo, hi))
+        s_ref, d_ref = state.copy(), diag.copy()
+        refs.append((s_ref, d_ref, port.integrate_state_vec(s_ref, d_ref, lo, hi, a, dt), s_dev, d_dev))
+    # an empty tile in the middle (its FABs are those of box 1; it contributes no cells and no statistics rows)
+    fs.insert(2, fs[1]); fd.insert(2, fd[1]); tiles.insert(2, capi.make_box((0, 0, 7), (-1, 5, 9)))
+    ncell = sum(s[0] * s[1] * s[2] for s in shapes)
+    csb = _cell_stats_buffer(ncell)
+    st = hc_lib.integrate_vec_batch(fs, fd, tiles, a, dt, cell_stats_ptr=csb.data_ptr())
+    torch.cuda.synchronize()
+    assert st.n_cells == ncell and st.n_failed == 0
+    cs = _cs_to_numpy(csb)
+    off = 0
+    for s_ref, d_ref, pst, s_dev, d_dev in refs:
+        n = len(pst)
+        assert np.array_equal(cs["nst"][off:off + n], pst[:, 0]) or np.mean(cs["nst"][off:off + n] == pst[:, 0]) > 0.99
+        assert np.abs(s_dev.cpu().numpy()[5] / s_ref[5] - 1).max() < E_T_TOL and np.abs(d_dev.cpu().numpy()[0] / d_ref[0] - 1).max() < E_T_TOL
+        off += n
+    assert st.sum_nst == int(cs["nst"].sum())
+
+
+def test_integrator_options_on_device(hc_lib, port):
+    """nyx.use_sundials_constraint (CVodeSetConstraints y > 0) and nyx.use_typical_steps (CVodeSetMaxStep(dt / old_max_steps)) on the GPU."""
+    torch = _torch()
+    z, n = 2.0, 20
+    a, dt = 1.0 / (1.0 + z), 0.5 * synth.step_dt(z)
+    lo, hi = (0, 0, 0), (n - 1, n - 1, n - 1)
+    for kw in (dict(use_constraint=1), dict(use_typical_steps=1, old_max_steps=5), dict(rtol=1e-6, atol_factor=1e-6)):
+        state, diag = synth.make_fab((n, n, n), seed=90, z=z)
+        s_dev, d_dev = torch.from_numpy(state).cuda(), torch.from_numpy(diag).cuda()
+        csb = _cell_stats_buffer(n ** 3)
+        st = hc_lib.integrate_vec_batch([capi.fab_of_torch(s_dev, lo)], [capi.fab_of_torch(d_dev, lo)], [capi.make_box(lo, hi)], a, dt,
+                                        params=hc_lib.default_params(**kw), cell_stats_ptr=csb.data_ptr())
+        torch.cuda.synchronize()
+        pst = port.integrate_state_vec(state, diag, lo, hi, a, dt, params=port.params(**kw))
+        cs = _cs_to_numpy(csb)
+        _compare_counts(cs, pst, f"options {kw}")
+        tol = 10.0 * kw.get("rtol", 1e-4)
+        assert np.abs(s_dev.cpu().numpy()[5] / state[5] - 1).max() < tol and np.abs(d_dev.cpu().numpy()[0] / diag[0] - 1).max() < tol
+        if "old_max_steps" in kw:
+            assert st.max_nst >= 5       # the step-size cap forces at least old_max_steps steps on every cell
+            assert int(cs["nst"].min()) >= 5
+
+
+def test_concurrent_calls_on_two_streams(hc_lib, port):
+    """The C-ABI is re-entrant per (thread, stream) (the SDC caller may run its MFIter loop under OpenMP): two host threads,
+    two streams, two different boxes at once; each result equals the one of a lone call bit for bit."""
+    import threading
+    torch = _torch()
+    z, n = 3.0, 40
+    a, dt = 1.0 / (1.0 + z), 0.5 * synth.step_dt(z)
+    lo, hi = (0, 0, 0), (n - 1, n - 1, n - 1)
+    fields = [synth.make_fab((n, n, n), seed=95 + i, z=z) for i in range(2)]
+
+    def run(i, stream, out):
+        s_dev, d_dev = torch.from_numpy(fields[i][0]).cuda(), torch.from_numpy(fields[i][1]).cuda()
+        torch.cuda.synchronize()
+        st = hc_lib.integrate_vec_batch([capi.fab_of_torch(s_dev, lo)], [capi.fab_of_torch(d_dev, lo)], [capi.make_box(lo, hi)], a, dt,
+                                        stream=stream.cuda_stream if stream is not None else None)
+        torch.cuda.synchronize()
+        out[i] = (s_dev.cpu().numpy(), d_dev.cpu().numpy(), st.as_dict())
+
+    alone, together = {}, {}
+    for i in range(2):
+        run(i, None, alone)
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    th = [threading.Thread(target=run, args=(i, streams[i], together)) for i in range(2)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    for i in range(2):
+        assert np.array_equal(alone[i][0], together[i][0]) and np.array_equal(alone[i][1], together[i][1]) and alone[i][2] == together[i][2]
