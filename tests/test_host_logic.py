@@ -77,6 +77,19 @@ def test_state_machine_struct_bitwise(harness, rates, port, z, seed, src, flash)
     assert util.stats_equal(cs, pst)
 
 
+def test_state_machine_inhomogeneous_reionization_bitwise(harness, rates, port):
+    n, z = 10, 5.5
+    d = util.inhomo_inputs(z, n, 341)
+    r = {k: (v.copy() if hasattr(v, "copy") else v) for k, v in d.items()}
+    lo, hi = (0, 0, 0), (n - 1, n - 1, n - 1)
+    pst = port.integrate_state_struct(r["s_old"], r["s_new"], r["diag"], r["hydro_src"], r["reset_src"], r["ir"], lo, hi,
+                                      d["a"], d["a_end"], d["dt"], 0, params=port.params(**d["kw"]))
+    cs = harness.integrate_struct(rates, d, lo, hi, 0, params=harness.params(**d["kw"]))
+    for k in ("s_old", "s_new", "diag", "ir"):
+        assert np.array_equal(d[k], r[k]), k
+    assert util.stats_equal(cs, pst)
+
+
 @pytest.mark.parametrize("kw", [dict(use_constraint=1), dict(use_typical_steps=1, old_max_steps=3), dict(max_steps=4),
                                 dict(rtol=1e-6, atol_factor=1e-6), dict(h_species=0.7)])
 def test_state_machine_options_bitwise(harness, rates, port, kw):

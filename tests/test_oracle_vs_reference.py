@@ -127,3 +127,32 @@ def test_compute_new_temp_bitwise(reference, port, max_temp_dt, large_temp):
     assert (diag[0] == 1.0e-2).any()                                           # the rho e <= 0 branch ran
     if max_temp_dt:
         assert (diag[0] == large_temp).any()                                   # and the clipping branch
+
+
+def test_inhomogeneous_reionization_bitwise(reference, port):
+    """nyx.inhomo_reion = 1: per-cell z_HI in diag component 2 decides the UVB switch and the instantaneous heating."""
+    from tests.golden.make_golden import FLASH_KEYS
+    n, z = 8, 5.5
+    d = util.inhomo_inputs(z, n, 331)
+    r = {k: (v.copy() if hasattr(v, "copy") else v) for k, v in d.items()}
+    lo, hi = (0, 0, 0), (n - 1, n - 1, n - 1)
+    reference.set("nyx.sundials_tile_size", "1 1 1")
+    reference.set("nyx.inhomo_reion", 1)
+    for k in ("zhi_flash", "T_zhi"):
+        reference.set(FLASH_KEYS[k], d["kw"][k])
+    reference.stats_reset()
+    try:
+        reference.integrate_state_struct([lo + hi], [r["s_old"]], [r["s_new"]], [r["diag"]], [r["hydro_src"]], [r["ir"]], [r["reset_src"]],
+                                         d["a"], d["a_end"], d["dt"], 0)
+    finally:
+        reference.set("nyx.sundials_tile_size", "1024000 8 8")
+        reference.set("nyx.inhomo_reion", 0)
+        reference.unset("nyx.inhomo_reion")
+        for k in ("zhi_flash", "T_zhi"):
+            reference.unset(FLASH_KEYS[k])
+    pst = port.integrate_state_struct(d["s_old"], d["s_new"], d["diag"], d["hydro_src"], d["reset_src"], d["ir"], lo, hi,
+                                      d["a"], d["a_end"], d["dt"], 0, params=port.params(**d["kw"]))
+    for k in ("s_old", "s_new", "diag", "ir"):
+        assert np.array_equal(d[k], r[k]), k
+    assert np.array_equal(reference.stats(), pst[:, :8])
+    assert not np.array_equal(d["s_new"][5], util.inhomo_inputs(z, n, 331)["s_new"][5])

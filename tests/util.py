@@ -31,6 +31,22 @@ def sdc_inputs(z, n, seed, src_scale=0.0):
     return dict(a=a, a_end=a_end, dt=dt, s_old=s_old, s_new=s_new, diag=diag, hydro_src=hs, reset_src=rs, ir=ir)
 
 
+def inhomo_inputs(z, n, seed, src_scale=0.05):
+    """sdc_inputs with a third diag component: the per-cell hydrogen reionization redshift z_HI (nyx.inhomo_reion = 1,
+    HC/f_rhs_struct.H:202-209,353-359): cells not yet reionized (z > z_HI: no UVB), cells reionized during this step
+    (z_end <= z_HI < z: heat injection towards T_zHI) and cells reionized earlier."""
+    d = sdc_inputs(z, n, seed, src_scale)
+    z_end = 1.0 / d["a_end"] - 1.0
+    rng = np.random.default_rng(seed + 1000)
+    u = rng.random((n, n, n))
+    zhi = np.where(u < 0.3, rng.uniform(z_end - 2.0, z_end - 1e-3, (n, n, n)),            # later: z > z_HI, JH = 0
+                   np.where(u < 0.6, rng.uniform(z_end, z - 1e-9, (n, n, n)),             # during this step
+                            rng.uniform(z + 1e-6, z + 3.0, (n, n, n))))                   # earlier
+    d["diag"] = np.ascontiguousarray(np.concatenate([d["diag"], zhi[None]], axis=0))
+    d["kw"] = dict(inhomo_reion=1, zhi_flash=6.0, T_zhi=2.0e4, zheii_flash=-1.0, T_zheii=0.0)
+    return d
+
+
 def eos_rows_inputs(n, seed, z=3.0):
     """A box for Nyx::compute_new_temp / reset_internal_energy: the synthetic LyA field plus momenta, a total energy that is (in
     parts of the box) inconsistent with rho e, cells with rho e <= 0, very hot cells (large_temp clipping) and stale diag(Ne)."""
