@@ -80,6 +80,10 @@ namespace {
 using namespace hc;
 
 constexpr int THREADS = HC_THREADS;
+#ifndef HC_EOS_THREADS
+#define HC_EOS_THREADS 512                 // threads per CTA of hc_eos_kernel, one CTA per SM (tables: 112 KB of shared memory); measured 256: 6.9, 384: 5.5, 512: 4.9, 768: 4.9 ms per 3.4e7 cells
+#endif
+constexpr int EOS_THREADS = HC_EOS_THREADS;
 constexpr int TAB_ROWS = NTAB + 1;         // one padding row: row j+1 always exists
 constexpr int CHUNK_MAX = 256;             // cells per work-queue chunk (a piece of one x-row of a tile)
 // dynamic shared memory: [ionx 2002 x 48 B][iony 2003 x 8 B, padded to 16][lane arrays ARR_DOUBLES x THREADS x 8 B]
@@ -374,7 +378,7 @@ __global__ void __launch_bounds__(THREADS, 1) hc_integrate_kernel(const __grid_c
 //   eos_mode 1: the cell body of Nyx::compute_new_temp (Source/Driver/Nyx.cpp:2473-2519): e = rho_e * (1 / rho); cells at or above
 //               large_temp are clipped (max_temp_dt), cells with rho_e <= 0 are reset to small_temp; both rewrite (rho e, rho E).
 // dstats: S_CELLS, S_EOS, S_NEITERS as for the integrators; S_FLOOR counts the cells reset to small_temp, S_FAILED the clipped ones.
-__global__ void __launch_bounds__(THREADS, 1) hc_eos_kernel(const __grid_constant__ KernelArgs a) {
+__global__ void __launch_bounds__(EOS_THREADS, 1) hc_eos_kernel(const __grid_constant__ KernelArgs a) {
     __shared__ unsigned long long s_stats[S_COUNT];
     double* s_ionx = reinterpret_cast<double*>(s_raw);
     double* s_iony = reinterpret_cast<double*>(s_raw + SM_IONX);
@@ -385,7 +389,7 @@ __global__ void __launch_bounds__(THREADS, 1) hc_eos_kernel(const __grid_constan
     const Consts& c = a.k;
     unsigned long long iters = 0, cells = 0, n_eos = 0, n_small = 0, n_large = 0;
     int ti = -1;
-    for (long long id = (long long)blockIdx.x * THREADS + threadIdx.x; id < a.ncells; id += (long long)gridDim.x * THREADS) {
+    for (long long id = (long long)blockIdx.x * EOS_THREADS + threadIdx.x; id < a.ncells; id += (long long)gridDim.x * EOS_THREADS) {
         ti = next_tile(a, ti, id);
         const TileDesc& t = a.tiles[ti];
         const HcFab& S = t.f[F_STATE];
@@ -663,7 +667,8 @@ int launch(int path, int ntiles, const HcFab* const* fabs, int nf, const HcBox* 
             hc_reset_e_kernel<<<g, 256, 0, stream>>>(a);
         } else {
             if (int rc = set_smem_attr(hc_eos_kernel, dt, 2, SMEM_EOS)) return rc;
-            hc_eos_kernel<<<grid, THREADS, SMEM_EOS, stream>>>(a);
+            const int ge = (int)std::min<long long>((ncells + EOS_THREADS - 1) / EOS_THREADS, dt.sm_count);
+            hc_eos_kernel<<<ge, EOS_THREADS, SMEM_EOS, stream>>>(a);
         }
     }
     CUDA_TRY(cudaGetLastError());
