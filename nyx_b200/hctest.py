@@ -1,7 +1,7 @@
 """The reference's `hctest` wire format: the isolation-test snapshot that Nyx::integrate_state_struct dumps with
 nyx.hctest_example_write = 1 and Exec/HeatCoolTests replays (Source/HeatCool/f_rhs_struct.H:587-697 sdc_writeOn / sdc_readFrom,
 Source/HeatCool/integrate_state_with_source_3d.cpp:82-125).  Reader and writer for test / bench harnesses, so that snapshots of real runs
-can be pushed through the CUDA path and the oracle (tools/hctest_replay.py); the dump/replay hooks themselves stay with the reference.
+can be pushed through the CUDA path (tools/hctest_replay.py; compared with the oracle in tests/test_hctest_format.py); the dump/replay hooks themselves stay with the reference.
 
 On disk, for step N and MFIter index i:
   <prefix>Chunk.N.i   six FABs back to back -- S_old, D_old, S_new, hydro_src, reset_src, IR (f_rhs_struct.H:639-644) -- each

@@ -1,7 +1,7 @@
-"""GPU diagnostic: cells whose CVODE flag differs from the oracle in the struct parity cases."""
+"""TEST INFRASTRUCTURE (diagnostics; the only place besides tests/, smoke() and bench.py's CPU arms that touches oracle/).  GPU diagnostic: cells whose CVODE flag differs from the oracle in the struct parity cases."""
 import os, sys
 import numpy as np, torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from nyx_b200 import capi, synth
 from oracle import pyref
 from tests import util

@@ -1,8 +1,8 @@
 #!/usr/bin/env python
-"""diagnostic: inhomogeneous-reionization SDC step, device vs oracle, where do the per-cell counters differ?"""
+"""TEST INFRASTRUCTURE (diagnostics; the only place besides tests/, smoke() and bench.py's CPU arms that touches oracle/).  diagnostic: inhomogeneous-reionization SDC step, device vs oracle, where do the per-cell counters differ?"""
 import os, sys
 import numpy as np, torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from nyx_b200 import capi, synth
 from oracle import pyref
 from tests import util

@@ -486,7 +486,7 @@ def test_inhomogeneous_reionization_on_device(hc_lib, port):
     n, z = 20, 5.5
     # (a pure reaction step: with random hydro sources a z ~ 5.5 box has ~0.5 % of cells whose forcing sits on the cooling equilibrium; there
     # the 1e-7 noise of the RHS -- the inner ne Newton exit -- defeats the finite-difference Jacobian, the integration thrashes through
-    # dozens of convergence failures in the oracle and on the GPU alike, and the outcome depends on last bits: tools/gpu_diag_inhomo.py)
+    # dozens of convergence failures in the oracle and on the GPU alike, and the outcome depends on last bits: tests/diag/gpu_diag_inhomo.py)
     d = util.inhomo_inputs(z, n, 351, src_scale=0.0)
     lo, hi = (0, 0, 0), (n - 1, n - 1, n - 1)
     names = ("s_old", "diag", "s_new", "hydro_src", "reset_src", "ir")
