@@ -1,5 +1,5 @@
 #!/bin/bash
-# final GPU session of a round: smoke(), parity tests, bench at 512^3 (N=1), reference arm, ncu launch list of the bench command,
+# GPU session of a round: smoke(), parity tests, bench at 512^3 (N=1), reference arm, ncu launch list of the bench command,
 # ncu --set full of the dominant kernel (256^3), SDC-path bench
 mkdir -p gpurun_out
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -1 gpurun_out/smoke.log
