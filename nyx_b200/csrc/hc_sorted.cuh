@@ -31,8 +31,28 @@ template <int PATH> constexpr int nd_total() { return ARR_DOUBLES + ND_COMMON + 
 // 32-bit words per lane: two packed words of small integers, 12 counters, 4 words of cell coordinates
 #define HC_SI_WORDS(X) X(nst) X(nstlp) X(nfe) X(nfe_ls) X(netf) X(nni) X(nnf) X(nsetups) X(ne_iters) X(attempts) X(n_eos) X(flag)
 constexpr int NI_WORDS = 2 + (0 HC_SI_WORDS(HC_COUNT)) + 4;
+#if !defined(HC_SORT_FINE)
+#define HC_SORT_FINE 1
+#endif
+#if HC_SORT_FINE
+// the step-completing lanes are split further by (order q, qwait), which decide loop trip counts and branches of their chain
+// (measured in one gpurun call, best of 6, twice: 68.43 / 68.48 ms against 69.48 / 71.87 ms with the 8 plain keys)
+constexpr int NSUB = 9;   // (min(q,3)-1) * 3 + (min(qwait,3)-1)
+enum Key { K_NEWTON = 0, K_LSETUP = NSUB, K_SETUP_REQ = 2 * NSUB, K_HIN, K_INIT, K_ETEST, K_FINAL, K_IDLE, NKEY };
+#else
+constexpr int NSUB = 1;
 constexpr int NKEY = 8;   // sort keys, in the order the warps will process them
 enum Key { K_NEWTON = 0, K_SETUP_REQ, K_LSETUP, K_HIN, K_INIT, K_ETEST, K_FINAL, K_IDLE };
+#endif
+static_assert(NKEY <= 32, "one lane per key in the base computation");
+// the 8 integrator phases behind the keys (diagnostics): NEWTON, SETUP_REQ, LSETUP, HIN, INIT, ETEST, FINAL, IDLE
+__device__ __forceinline__ int key_class(int key) {
+#if HC_SORT_FINE
+    return (key < K_LSETUP) ? 0 : (key < K_SETUP_REQ) ? 2 : (key == K_SETUP_REQ) ? 1 : 3 + (key - K_HIN);
+#else
+    return key;
+#endif
+}
 
 template <int PATH, int LANES>
 struct Layout {
@@ -56,9 +76,15 @@ template <class LaneT>
 __device__ __forceinline__ int sort_key(unsigned w0, unsigned w1) {
     const int pc = (int)(w0 & 15u);
     const bool callSetup = (w1 >> 8) & 1u, res_at_top = (w1 >> 9) & 1u;
+#if HC_SORT_FINE
+    const int q = (int)((w0 >> 4) & 15u), qwait = (int)((w0 >> 12) & 15u);
+    const int sub = (min(max(q, 1), 3) - 1) * 3 + (min(max(qwait, 1), 3) - 1);
+#else
+    const int sub = 0;
+#endif
     switch (pc) {
-    case PC_NLS_RES: return (res_at_top && callSetup) ? K_SETUP_REQ : K_NEWTON;
-    case PC_LSETUP_F: return K_LSETUP;
+    case PC_NLS_RES: return (res_at_top && callSetup) ? K_SETUP_REQ : K_NEWTON + sub;
+    case PC_LSETUP_F: return K_LSETUP + sub;
     case PC_HIN_F: return K_HIN;
     case PC_INIT_F0: return K_INIT;
     case PC_ETEST_F: return K_ETEST;
@@ -162,7 +188,7 @@ __global__ void __launch_bounds__(LANES, HC_SORTED_CTAS) hc_sorted_kernel(const 
 #if defined(HC_PHASE_TIMING)
             if (rank == 0) {
 #pragma unroll
-                for (int kk = 0; kk < NKEY; ++kk) if (key == kk) ph[8 + kk] += __popc(same);
+                for (int kk = 0; kk < 8; ++kk) if (key_class(key) == kk) ph[8 + kk] += __popc(same);
             }
             ph[0] += 1;
 #endif
@@ -200,12 +226,12 @@ __global__ void __launch_bounds__(LANES, HC_SORTED_CTAS) hc_sorted_kernel(const 
             HC_TICK(16);
 #if defined(HC_PHASE_TIMING)
             const long long t_b0 = clock64();
-            const int key0 = __shfl_sync(0xffffffffu, sort_key<LaneT>(w0, w1), 0);
+            const int key0 = key_class(__shfl_sync(0xffffffffu, sort_key<LaneT>(w0, w1), 0));
 #endif
             const bool act0 = ln.active();
             const unsigned rmask = __ballot_sync(0xffffffffu, act0);
 #if defined(HC_PHASE_TIMING)
-            ln.dbg_on = (key0 == K_LSETUP) && (__shfl_sync(0xffffffffu, sort_key<LaneT>(w0, w1), 31) == K_LSETUP);   // warps made of Jacobian-setup lanes only
+            ln.dbg_on = (key0 == 2) && (key_class(__shfl_sync(0xffffffffu, sort_key<LaneT>(w0, w1), 31)) == 2);   // warps made of Jacobian-setup lanes only
             ln.dbg_last = clock64();
 #endif
             if (act0) {
@@ -268,7 +294,7 @@ __global__ void __launch_bounds__(LANES, HC_SORTED_CTAS) hc_sorted_kernel(const 
                 const long long t_b1 = clock64();
                 const int nact = __popc(rmask);
 #pragma unroll
-                for (int kk = 0; kk < NKEY; ++kk) if (key0 == kk) { ph[24 + kk] += (unsigned long long)(t_b1 - t_b0); ph[32 + kk] += 1; ph[40 + kk] += nact; }
+                for (int kk = 0; kk < 8; ++kk) if (key0 == kk) { ph[24 + kk] += (unsigned long long)(t_b1 - t_b0); ph[32 + kk] += 1; ph[40 + kk] += nact; }
             }
 #endif
         }
