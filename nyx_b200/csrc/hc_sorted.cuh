@@ -231,7 +231,10 @@ __global__ void __launch_bounds__(LANES, HC_SORTED_CTAS) hc_sorted_kernel(const 
             const bool act0 = ln.active();
             const unsigned rmask = __ballot_sync(0xffffffffu, act0);
 #if defined(HC_PHASE_TIMING)
-            ln.dbg_on = (key0 == 2) && (key_class(__shfl_sync(0xffffffffu, sort_key<LaneT>(w0, w1), 31)) == 2);   // warps made of Jacobian-setup lanes only
+#if !defined(HC_DBG_CLASS)
+#define HC_DBG_CLASS 2   // 0: Newton-residual lanes, 2: Jacobian-setup lanes
+#endif
+            ln.dbg_on = (key0 == HC_DBG_CLASS) && (key_class(__shfl_sync(0xffffffffu, sort_key<LaneT>(w0, w1), 31)) == HC_DBG_CLASS);   // stage timing: warps made of one phase only
             ln.dbg_last = clock64();
 #endif
             if (act0) {
