@@ -32,11 +32,12 @@ template <int PATH> constexpr int nd_total() { return ARR_DOUBLES + ND_COMMON + 
 #define HC_SI_WORDS(X) X(nst) X(nstlp) X(nfe) X(nfe_ls) X(netf) X(nni) X(nnf) X(nsetups) X(ne_iters) X(attempts) X(n_eos) X(flag)
 constexpr int NI_WORDS = 2 + (0 HC_SI_WORDS(HC_COUNT)) + 4;
 #if !defined(HC_SORT_FINE)
-#define HC_SORT_FINE 1
+#define HC_SORT_FINE 2
 #endif
 #if HC_SORT_FINE
 // the step-completing lanes are split further by (order q, qwait), which decide loop trip counts and branches of their chain
-// (measured in one gpurun call, best of 6, twice: 68.43 / 68.48 ms against 69.48 / 71.87 ms with the 8 plain keys)
+// (measured in one gpurun call, best of 6, twice: 68.43 / 68.48 ms against 69.48 / 71.87 ms with the 8 plain keys; HC_SORT_FINE == 2
+// interleaves the two step-completing phases within each (q, qwait) class: 62.15 / 61.60 ms against 64.66 / 65.86 ms for == 1)
 constexpr int NSUB = 9;   // (min(q,3)-1) * 3 + (min(qwait,3)-1)
 enum Key { K_NEWTON = 0, K_LSETUP = NSUB, K_SETUP_REQ = 2 * NSUB, K_HIN, K_INIT, K_ETEST, K_FINAL, K_IDLE, NKEY };
 #else
@@ -47,7 +48,9 @@ enum Key { K_NEWTON = 0, K_SETUP_REQ, K_LSETUP, K_HIN, K_INIT, K_ETEST, K_FINAL,
 static_assert(NKEY <= 32, "one lane per key in the base computation");
 // the 8 integrator phases behind the keys (diagnostics): NEWTON, SETUP_REQ, LSETUP, HIN, INIT, ETEST, FINAL, IDLE
 __device__ __forceinline__ int key_class(int key) {
-#if HC_SORT_FINE
+#if HC_SORT_FINE == 2
+    return (key < K_SETUP_REQ) ? ((key & 1) ? 2 : 0) : (key == K_SETUP_REQ) ? 1 : 3 + (key - K_HIN);
+#elif HC_SORT_FINE
     return (key < K_LSETUP) ? 0 : (key < K_SETUP_REQ) ? 2 : (key == K_SETUP_REQ) ? 1 : 3 + (key - K_HIN);
 #else
     return key;
@@ -83,8 +86,15 @@ __device__ __forceinline__ int sort_key(unsigned w0, unsigned w1) {
     const int sub = 0;
 #endif
     switch (pc) {
+#if HC_SORT_FINE == 2
+    // the two step-completing phases interleaved: key = 2 * (q, qwait class) + phase, so that a Newton-residual lane sits next to the
+    // Jacobian-setup lanes of the same order -- they differ in their first two stages only and share the long tail of the chain
+    case PC_NLS_RES: return (res_at_top && callSetup) ? K_SETUP_REQ : K_NEWTON + 2 * sub;
+    case PC_LSETUP_F: return K_NEWTON + 2 * sub + 1;
+#else
     case PC_NLS_RES: return (res_at_top && callSetup) ? K_SETUP_REQ : K_NEWTON + sub;
     case PC_LSETUP_F: return K_LSETUP + sub;
+#endif
     case PC_HIN_F: return K_HIN;
     case PC_INIT_F0: return K_INIT;
     case PC_ETEST_F: return K_ETEST;
