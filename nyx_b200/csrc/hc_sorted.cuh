@@ -178,7 +178,9 @@ __global__ void __launch_bounds__(LANES, HC_SORTED_CTAS) hc_sorted_kernel(const 
             if (lane_id < NKEY) s_cnt[lane_id * L::WARPS + warp] = 0;
             __syncwarp();
             if (rank == 0) s_cnt[key * L::WARPS + warp] = __popc(same);
+            HC_TICK(20);
             __syncthreads();
+            HC_TICK(21);
             // every warp computes its own bases: lane kk sums the counts of key kk over the warps (and over the warps before this one)
             int tot_k = 0, pre_k = 0;
             if (lane_id < NKEY) {
@@ -194,6 +196,7 @@ __global__ void __launch_bounds__(LANES, HC_SORTED_CTAS) hc_sorted_kernel(const 
             for (int o = 1; o < NKEY; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane_id >= o) incl += t; }
             const int base_k = incl - tot_k + pre_k;   // first position of this warp's lanes with key == lane_id
             s_order[__shfl_sync(0xffffffffu, base_k, key) + rank] = (unsigned short)tid;
+            HC_TICK(22);
             __syncthreads();
 #if defined(HC_PHASE_TIMING)
             if (rank == 0) {

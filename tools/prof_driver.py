@@ -39,9 +39,11 @@ if hasattr(hc.lib, "hc_debug_phase"):
     rw = max(v[0], 1)
     tot = max(v[7], 1)
     print(f"phase timing (sum over {reps} reps): warp-rounds {v[0]}  cycles per warp-round {v[7] / rw:.0f}")
+    v[1] += v[20] + v[21] + v[22]   # the sort phase: keys + counts, barrier, bases + order, barrier
     names = {1: "sort", 16: "B load", 17: "B resume+store", 18: "B refill", 19: "B writeback", 3: "B barrier wait", 4: "R work", 5: "R barrier wait"}
     for k, nm in names.items():
         print(f"  {nm:18s} {100.0 * v[k] / tot:6.2f} %   {v[k] / rw:9.0f} cycles per warp-round")
+    print(f"  sort split: keys+counts {v[20] / rw:.0f}, barrier {v[21] / rw:.0f}, bases+order {v[22] / rw:.0f}, final barrier (+ first instructions of phase B) {(v[1] - v[20] - v[21] - v[22]) / rw:.0f} cycles per warp-round")
     print(f"  active lanes at R per warp-round: {v[6] / rw:.2f} / 32")
     keys = ["NEWTON", "SETUP_REQ", "LSETUP", "HIN", "INIT", "ETEST", "FINAL", "IDLE"]
     print("  lanes per key per warp-round: " + ", ".join(f"{k}={v[8 + i] / rw:.2f}" for i, k in enumerate(keys)))
