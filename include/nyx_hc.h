@@ -13,6 +13,10 @@
  *   hc_eos_T_given_Re                      <- nyx_eos_T_given_Re_device over a box  Source/EOS/eos_hc.H:190-220
  *   hc_compute_new_temp_batch              <- Nyx::compute_new_temp                 Source/Driver/Nyx.cpp:2435-2522
  *   hc_reset_internal_energy_batch         <- Nyx::reset_internal_energy            Source/Driver/Nyx.cpp:2356-2385, Source/EOS/reset_internal_e.H:16-68
+ *   hc_update_state_with_sources_batch     <- Nyx::update_state_with_sources (SDC) Source/TimeStep/Nyx_update_state_with_sources.cpp:9-121
+ *   hc_enforce_minimum_density_batch       <- Nyx::enforce_minimum_density, floor   Source/TimeStep/Nyx_enforce_minimum_density.cpp:8-107,
+ *                                             floor_density                         Source/TimeStep/Nyx_enforce_minimum_density.H:8-58
+ *   hc_fab_copy|add|subtract_batch         <- MultiFab::Copy / Add / Subtract around the call  Source/Hydro/sdc_hydro.cpp:83-84,94-95,112,135
  *   HcParams                               <- the nyx.* run-time flags of the path, Source/Driver/Nyx.cpp:116-181,
  *                                             Source/HeatCool/f_rhs_struct.H:45-101
  *   HcStats                                <- CVodeGetNum* counters (integrate_state_with_source_3d.cpp:755-790) and the
@@ -158,6 +162,44 @@ int hc_compute_new_temp_host(int ntiles, const HcFab* state, const HcFab* diag, 
                              double small_temp, double large_temp, int max_temp_dt, HcStats* stats);
 int hc_reset_internal_energy_host(int ntiles, const HcFab* state, const HcFab* diag, const HcFab* reset_src, const HcBox* tiles, double a,
                                   const HcParams* prm, double small_temp, int interp);
+
+/* ---- the SDC source assembly either side of sdc_reactions -------------------------------------------------------- */
+enum { HC_MIN_DENSITY_FLOOR = 0, HC_MIN_DENSITY_CONSERVATIVE = 1 };
+typedef struct HcSrcParams {
+    double small_dens;        /* nyx.small_dens */
+    double small_temp;        /* nyx.small_temp */
+    double gamma_minus_1;     /* nyx.gamma - 1 */
+    double h_species;         /* nyx.h_species */
+    int min_density_type;     /* nyx.enforce_min_density_type: "floor" (default) = HC_MIN_DENSITY_FLOOR.  "conservative" moves density between
+                                 neighbour cells through the host framework's FillPatch and is rejected with HC_ERR_ARG */
+    int sdc;                  /* 1: the reference's SDC build (enforce_minimum_density also resets hydro_src(rho)); 0: the non-SDC build */
+} HcSrcParams;
+void hc_default_src_params(HcSrcParams* p);
+
+/* Nyx::update_state_with_sources (Source/TimeStep/Nyx_update_state_with_sources.cpp:9-121) for all tiles of this rank in one call:
+ * S_new = source update of S_old (:33-76); Nyx::enforce_minimum_density, floor variant, decided by the minimum of the new density over
+ * THE TILES OF THIS CALL (:79-84); gravity update (:90-120).  Six-component state FABs (CONST_SPECIES), grav 3 components; argument order
+ * of the reference (reset_e_src is not touched by the floor variant and is not an argument).
+ * min_dens (may be NULL): the minimum new density before the floor.  NULL: nothing is read back, the call is asynchronous on `stream`.
+ * Several ranks: pass min_dens, reduce it over ranks (the reference's S_new.min() is a global reduction) and, where the global minimum is
+ * below small_dens but the local one was not, call hc_enforce_minimum_density_batch with the same arguments. */
+int hc_update_state_with_sources_batch(int ntiles, const HcFab* s_old, const HcFab* s_new, const HcFab* ext_src_old, const HcFab* hydro_src,
+                                       const HcFab* grav, const HcBox* tiles, double dt, double a_old, double a_new, const HcSrcParams* prm,
+                                       double* min_dens, void* stream);
+/* The enforce branch unconditionally: every cell recomputed from the (untouched) inputs with floor_density between the source and the
+ * gravity updates; hydro_src(rho) = S_new(rho) - S_old(rho) when prm->sdc.  At most once per update (it rewrites hydro_src(rho)). */
+int hc_enforce_minimum_density_batch(int ntiles, const HcFab* s_old, const HcFab* s_new, const HcFab* ext_src_old, const HcFab* hydro_src,
+                                     const HcFab* grav, const HcBox* tiles, double dt, double a_old, double a_new, const HcSrcParams* prm,
+                                     void* stream);
+int hc_update_state_with_sources_host(int ntiles, const HcFab* s_old, const HcFab* s_new, const HcFab* ext_src_old, const HcFab* hydro_src,
+                                      const HcFab* grav, const HcBox* tiles, double dt, double a_old, double a_new, const HcSrcParams* prm,
+                                      double* min_dens);
+int hc_enforce_minimum_density_host(int ntiles, const HcFab* s_old, const HcFab* s_new, const HcFab* ext_src_old, const HcFab* hydro_src,
+                                    const HcFab* grav, const HcBox* tiles, double dt, double a_old, double a_new, const HcSrcParams* prm);
+/* MultiFab::Copy / Add / Subtract (dst, src, scomp, dcomp, ncomp, nghost = tiles): dst(dcomp + n) {=, +=, -=} src(scomp + n) over the tiles */
+int hc_fab_copy_batch(int ntiles, const HcFab* dst, int dcomp, const HcFab* src, int scomp, int ncomp, const HcBox* tiles, void* stream);
+int hc_fab_add_batch(int ntiles, const HcFab* dst, int dcomp, const HcFab* src, int scomp, int ncomp, const HcBox* tiles, void* stream);
+int hc_fab_subtract_batch(int ntiles, const HcFab* dst, int dcomp, const HcFab* src, int scomp, int ncomp, const HcBox* tiles, void* stream);
 
 /* measured FP64 FMA throughput of the current device in FLOP/s (2 flops per DFMA), for roofline denominators */
 int hc_measure_fp64_peak(double* flops_per_s);

@@ -32,6 +32,11 @@ class HcParams(C.Structure):
                 ("use_typical_steps", C.c_int), ("use_constraint", C.c_int), ("inhomo_reion", C.c_int), ("pad_", C.c_int)]
 
 
+class HcSrcParams(C.Structure):
+    _fields_ = [("small_dens", C.c_double), ("small_temp", C.c_double), ("gamma_minus_1", C.c_double), ("h_species", C.c_double),
+                ("min_density_type", C.c_int), ("sdc", C.c_int)]
+
+
 STATS_FIELDS = ("n_cells", "n_failed", "n_floor", "sum_nst", "max_nst", "sum_nfe", "sum_nfe_ls", "sum_netf", "sum_nni",
                 "sum_ncfn", "sum_nsetups", "sum_ne_iters", "sum_attempts", "sum_eos")
 
@@ -104,6 +109,14 @@ def declare(lib, prefix="hc_"):
     lib.hc_reset_internal_energy_host.argtypes = [C.c_int, fp, fp, fp, bp, C.c_double, pp, C.c_double, C.c_int]
     lib.hc_integrate_vec_host.argtypes = [C.c_int, fp, fp, bp, C.c_double, C.c_double, pp, sp]
     lib.hc_integrate_struct_host.argtypes = [C.c_int] + [fp] * 6 + [bp, C.c_double, C.c_double, C.c_double, C.c_int, pp, sp]
+    qp = C.POINTER(HcSrcParams)
+    lib.hc_default_src_params.argtypes = [qp]
+    lib.hc_update_state_with_sources_batch.argtypes = [C.c_int] + [fp] * 5 + [bp, C.c_double, C.c_double, C.c_double, qp, _dp, C.c_void_p]
+    lib.hc_enforce_minimum_density_batch.argtypes = [C.c_int] + [fp] * 5 + [bp, C.c_double, C.c_double, C.c_double, qp, C.c_void_p]
+    lib.hc_enforce_minimum_density_host.argtypes = [C.c_int] + [fp] * 5 + [bp, C.c_double, C.c_double, C.c_double, qp]
+    lib.hc_update_state_with_sources_host.argtypes = [C.c_int] + [fp] * 5 + [bp, C.c_double, C.c_double, C.c_double, qp, _dp]
+    for name in ("hc_fab_copy_batch", "hc_fab_add_batch", "hc_fab_subtract_batch"):
+        getattr(lib, name).argtypes = [C.c_int, fp, C.c_int, fp, C.c_int, C.c_int, bp, C.c_void_p]
     lib.hc_measure_fp64_peak.argtypes = [_dp]
     lib.hc_selftest_log10.argtypes = [_dp, _dp, C.POINTER(C.c_int), C.c_longlong]
     lib.hc_sync.argtypes = [C.c_void_p]
@@ -209,6 +222,38 @@ class NyxHC:
         p = params or self.default_params()
         self.check(self.lib.hc_reset_internal_energy_batch(len(tiles), self._arr(state_fabs, HcFab), self._arr(diag_fabs, HcFab),
                                                            self._arr(reset_fabs, HcFab), self._arr(tiles, HcBox), a, C.byref(p), small_temp, interp, stream))
+
+    def src_params(self, **kw):
+        p = HcSrcParams()
+        self.lib.hc_default_src_params(C.byref(p))
+        for k, v in kw.items():
+            setattr(p, k, v)
+        return p
+
+    def update_state_with_sources_batch(self, s_old, s_new, ext_src, hydro_src, grav, tiles, dt, a_old, a_new, params, want_min=True,
+                                        stream=None, host=False):
+        """Nyx::update_state_with_sources over all tiles; returns the minimum new density before the floor (None if not wanted)"""
+        arrs = [self._arr(x, HcFab) for x in (s_old, s_new, ext_src, hydro_src, grav)]
+        m = C.c_double(0.0)
+        mp = C.byref(m) if want_min else None
+        if host:
+            self.check(self.lib.hc_update_state_with_sources_host(len(tiles), *arrs, self._arr(tiles, HcBox), dt, a_old, a_new, C.byref(params), mp))
+        else:
+            self.check(self.lib.hc_update_state_with_sources_batch(len(tiles), *arrs, self._arr(tiles, HcBox), dt, a_old, a_new, C.byref(params), mp,
+                                                                   stream))
+        return m.value if want_min else None
+
+    def enforce_minimum_density_batch(self, s_old, s_new, ext_src, hydro_src, grav, tiles, dt, a_old, a_new, params, stream=None, host=False):
+        arrs = [self._arr(x, HcFab) for x in (s_old, s_new, ext_src, hydro_src, grav)]
+        if host:
+            self.check(self.lib.hc_enforce_minimum_density_host(len(tiles), *arrs, self._arr(tiles, HcBox), dt, a_old, a_new, C.byref(params)))
+            return
+        self.check(self.lib.hc_enforce_minimum_density_batch(len(tiles), *arrs, self._arr(tiles, HcBox), dt, a_old, a_new, C.byref(params), stream))
+
+    def fab_op_batch(self, op, dst, dcomp, src, scomp, ncomp, tiles, stream=None):
+        """op in ("copy", "add", "subtract"): MultiFab::Copy / Add / Subtract of a component range over the tiles"""
+        fn = getattr(self.lib, f"hc_fab_{op}_batch")
+        self.check(fn(len(tiles), self._arr(dst, HcFab), dcomp, self._arr(src, HcFab), scomp, ncomp, self._arr(tiles, HcBox), stream))
 
     def selftest_log10(self, x):
         """log10 of a float64 array through the kernels' table-driven fast path -> (y, bad)"""

@@ -1,0 +1,173 @@
+// hc_sources.cuh -- SURVEY section 8f rank 2: the SDC source assembly either side of sdc_reactions, as ONE streaming sweep.
+//
+// Reference behaviour (three sweeps over the level, Source/TimeStep/Nyx_update_state_with_sources.cpp):
+//   (1) :33-76    S_new(n) = f_n(S_old(n), hydro_src(n), ext_src_old(n)) for every state component
+//   (2) :79-84    Nyx::enforce_minimum_density (Nyx_enforce_minimum_density.cpp:8-65): ONLY IF the minimum of the new density over the
+//                 whole level is below small_dens: floor_density (Nyx_enforce_minimum_density.H:8-58) in the cells below it and, in the
+//                 SDC build, hydro_src(rho) = S_new(rho) - S_old(rho) in EVERY cell (:40-63)
+//   (3) :90-120   gravity: momenta += rho_old g dt / a_new, rho E += (rho u)_old . g dt a_half / a_new^2
+// All three are cell-local; only the decision of (2) is global.  Here: hc_sources_kernel<false> does (1) + (3) in registers, stores S_new
+// once and reduces the minimum of the sweep-(1) density into one word; hc_sources_kernel<true> recomputes a cell from the untouched
+// inputs with (2) in between, and is either predicated on that word (single rank: no host round trip) or launched by the caller after
+// the minimum has been reduced over ranks.  Per cell: 21 doubles read, 6 written = 216 algorithmic bytes (the reference's three sweeps
+// move 192 + 120 + (2) bytes); HBM-bound, arithmetic is the reference's expression by expression (-fmad=false).
+//
+// Included by nyx_hc.cu inside its anonymous namespace (uses TileDesc, fab_off, cell_of).
+#ifndef NYXB200_HC_SOURCES_CUH
+#define NYXB200_HC_SOURCES_CUH
+
+enum SrcSlot { SRC_UIN = 0, SRC_UOUT = 1, SRC_EXT = 2, SRC_HSRC = 3, SRC_GRAV = 4 };
+
+struct SrcArgs {
+    const TileDesc* tiles;
+    int ntiles;
+    long long ncells;
+    unsigned long long* min_key;   // ordered-integer image of the minimum new density (see dens_key)
+    int use_flag;                  // <true> kernel: return at once unless *min_key decodes below small_dens
+    int sdc;                       // SDC build of the reference: (2) resets hydro_src(rho)
+    double dt, a_old, a_half, a_half_inv, a_oldsq, a_newsq, a_new_inv, a_newsq_inv, dt_a_new, a_half_dt, dt_a_half;
+    double small_dens, floor_rhoe; // floor_rhoe = small_dens * e(small_temp, Ne = 0)
+};
+
+// doubles ordered as unsigned integers: key(x) < key(y) <=> x < y (no NaNs reach this: they fail the `<` that guards the update)
+__host__ __device__ __forceinline__ unsigned long long dens_key(double x) {
+#if defined(__CUDA_ARCH__)
+    const unsigned long long b = (unsigned long long)__double_as_longlong(x);
+#else
+    unsigned long long b; memcpy(&b, &x, 8);
+#endif
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__host__ __device__ __forceinline__ double dens_from_key(unsigned long long k) {
+    const unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+#if defined(__CUDA_ARCH__)
+    return __longlong_as_double((long long)b);
+#else
+    double x; memcpy(&x, &b, 8); return x;
+#endif
+}
+
+constexpr int SRC_THREADS = 256;
+constexpr int SRC_U = 2;            // cells per thread and pass: 42 loads in flight before the first store
+
+template <bool ENFORCE>
+__global__ void __launch_bounds__(SRC_THREADS) hc_sources_kernel(const __grid_constant__ SrcArgs a) {
+    if (ENFORCE && a.use_flag) {
+        if (!(dens_from_key(*a.min_key) < a.small_dens)) return;
+    }
+    double vmin = DBL_MAX;   // amrex::MultiFab::min starts from std::numeric_limits<Real>::max()
+    int t0 = -1;
+    for (long long base = (long long)blockIdx.x * (SRC_THREADS * SRC_U); base < a.ncells; base += (long long)gridDim.x * (SRC_THREADS * SRC_U)) {
+        if (t0 < 0) t0 = find_tile_by_cell(a.tiles, a.ntiles, base);
+        while (t0 + 1 < a.ntiles && a.tiles[t0 + 1].offset <= base) ++t0;
+        double ui[SRC_U][6], hs[SRC_U][6], ex[SRC_U][6], g[SRC_U][3];
+        double* po[SRC_U]; double* ph[SRC_U];
+        long long nso[SRC_U];
+        bool on[SRC_U];
+#pragma unroll
+        for (int u = 0; u < SRC_U; ++u) {
+            const long long id = base + u * SRC_THREADS + threadIdx.x;
+            on[u] = id < a.ncells;
+            po[u] = nullptr; ph[u] = nullptr; nso[u] = 0;
+            if (on[u]) {
+                int ti = t0;
+                while (ti + 1 < a.ntiles && a.tiles[ti + 1].offset <= id) ++ti;
+                const TileDesc& t = a.tiles[ti];
+                int i, j, k;
+                cell_of(t, id, i, j, k);
+                const HcFab& Fi = t.f[SRC_UIN]; const HcFab& Fo = t.f[SRC_UOUT]; const HcFab& Fe = t.f[SRC_EXT];
+                const HcFab& Fh = t.f[SRC_HSRC]; const HcFab& Fg = t.f[SRC_GRAV];
+                const double* pi = Fi.p + fab_off(Fi, i, j, k);
+                const double* pe = Fe.p + fab_off(Fe, i, j, k);
+                const double* pg = Fg.p + fab_off(Fg, i, j, k);
+                ph[u] = Fh.p + fab_off(Fh, i, j, k);
+                po[u] = Fo.p + fab_off(Fo, i, j, k); nso[u] = Fo.nstride;
+#pragma unroll
+                for (int n = 0; n < 6; ++n) { ui[u][n] = __ldg(pi + n * Fi.nstride); hs[u][n] = ph[u][n * Fh.nstride]; ex[u][n] = __ldg(pe + n * Fe.nstride); }
+#pragma unroll
+                for (int n = 0; n < 3; ++n) g[u][n] = __ldg(pg + n * Fg.nstride);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < SRC_U; ++u) {
+            if (!on[u]) continue;
+            double o[6];
+            // sweep (1), Nyx_update_state_with_sources.cpp:47-73
+            o[0] = ui[u][0] + hs[u][0] + a.dt * ex[u][0] * a.a_half_inv;
+#pragma unroll
+            for (int n = 1; n <= 3; ++n) {
+                o[n] = a.a_old * ui[u][n] + hs[u][n] + a.dt * ex[u][n];
+                o[n] = o[n] * a.a_new_inv;
+            }
+#pragma unroll
+            for (int n = 4; n <= 5; ++n) {
+                o[n] = a.a_oldsq * ui[u][n] + hs[u][n] + a.a_half_dt * ex[u][n];
+                o[n] = o[n] * a.a_newsq_inv;
+            }
+            if (!ENFORCE) {
+                if (o[0] < vmin) vmin = o[0];
+            } else {
+                // sweep (2): floor_density, then (SDC) hydro_src(rho) = A_rho in every cell
+                if (o[0] < a.small_dens) {
+                    o[0] = a.small_dens;
+                    o[1] = 0.0; o[2] = 0.0; o[3] = 0.0;
+                    o[5] = a.floor_rhoe;
+                    o[4] = o[5];
+                }
+                if (a.sdc) ph[u][0] = o[0] - ui[u][0];
+            }
+            // sweep (3), :97-119 (rho and the momenta of the OLD state)
+            const double rho = ui[u][0];
+            const double SrU = rho * g[u][0], SrV = rho * g[u][1], SrW = rho * g[u][2];
+            o[1] += SrU * a.dt_a_new;
+            o[2] += SrV * a.dt_a_new;
+            o[3] += SrW * a.dt_a_new;
+            const double SrE = ui[u][1] * g[u][0] + ui[u][2] * g[u][1] + ui[u][3] * g[u][2];
+            o[4] = (a.a_newsq * o[4] + SrE * a.dt_a_half) * a.a_newsq_inv;
+#pragma unroll
+            for (int n = 0; n < 6; ++n) po[u][n * nso[u]] = o[n];
+        }
+    }
+    if (!ENFORCE) {
+        // block minimum -> one atomicMin per CTA
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) { const double w = __shfl_xor_sync(0xffffffffu, vmin, s); if (w < vmin) vmin = w; }
+        __shared__ double s_min[SRC_THREADS / 32];
+        if ((threadIdx.x & 31) == 0) s_min[threadIdx.x >> 5] = vmin;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double m = s_min[0];
+#pragma unroll
+            for (int w = 1; w < SRC_THREADS / 32; ++w) if (s_min[w] < m) m = s_min[w];
+            atomicMin(a.min_key, dens_key(m));
+        }
+    }
+}
+
+// MultiFab::Copy / Add / Subtract of one component range (Source/Hydro/sdc_hydro.cpp:83-84,94-95,112,135): dst(dcomp + n) (=, +=, -=) src(scomp + n)
+struct FabOpArgs {
+    const TileDesc* tiles;
+    int ntiles;
+    long long ncells;
+    int scomp, dcomp, ncomp, op;   // op 0: copy, 1: add, 2: subtract
+};
+__global__ void __launch_bounds__(256) hc_fab_op_kernel(const __grid_constant__ FabOpArgs a) {
+    int t0 = -1;
+    for (long long id = (long long)blockIdx.x * 256 + threadIdx.x; id < a.ncells; id += (long long)gridDim.x * 256) {
+        if (t0 < 0) t0 = find_tile_by_cell(a.tiles, a.ntiles, id);
+        while (t0 + 1 < a.ntiles && a.tiles[t0 + 1].offset <= id) ++t0;
+        const TileDesc& t = a.tiles[t0];
+        int i, j, k;
+        cell_of(t, id, i, j, k);
+        const HcFab& D = t.f[0]; const HcFab& S = t.f[1];
+        double* pd = D.p + fab_off(D, i, j, k) + (long long)a.dcomp * D.nstride;
+        const double* ps = S.p + fab_off(S, i, j, k) + (long long)a.scomp * S.nstride;
+        for (int n = 0; n < a.ncomp; ++n) {
+            const double s = ps[n * S.nstride];
+            double* d = pd + n * D.nstride;
+            if (a.op == 0) *d = s; else if (a.op == 1) *d = *d + s; else *d = *d - s;
+        }
+    }
+}
+
+#endif

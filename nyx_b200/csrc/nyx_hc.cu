@@ -17,7 +17,10 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdint>
+#include <cfloat>
 #include <cstdio>
+#include <cstring>
+#include <functional>
 #include <mutex>
 #include <vector>
 
@@ -507,6 +510,7 @@ __global__ void __launch_bounds__(256) hc_reset_e_kernel(const __grid_constant__
     }
 }
 
+#include "hc_sources.cuh"
 #include "hc_sorted.cuh"
 
 // FP64 FMA throughput probe: 8 independent chains per thread, explicit __fma_rn (unaffected by -fmad=false)
@@ -714,7 +718,9 @@ int host_pipe(int dev, HostPipe*& hp) {
     return HC_OK;
 }
 
-int run_host(int path, int ntiles, std::vector<HostSlot>& slots, const HcBox* tiles, const Consts& k, HcStats* stats, const EosOpts* eos = nullptr) {
+using GroupLauncher = std::function<int(int n, const HcFab* const* fabs, const HcBox* tiles, cudaStream_t stream)>;
+int run_host(int path, int ntiles, std::vector<HostSlot>& slots, const HcBox* tiles, const Consts& k, HcStats* stats, const EosOpts* eos = nullptr,
+             const GroupLauncher* custom = nullptr) {
     int dev; if (int rc = current_device(dev)) return rc;
     HostPipe* hp = nullptr;
     if (int rc = host_pipe(dev, hp)) return rc;
@@ -762,7 +768,8 @@ int run_host(int path, int ntiles, std::vector<HostSlot>& slots, const HcBox* ti
         CUDA_TRY(cudaStreamWaitEvent(hp->comp, e_in, 0));
         std::vector<const HcFab*> fabs(nf);
         for (int s = 0; s < nf; ++s) fabs[s] = dfab[s].data();
-        rc = launch(path, n, fabs.data(), nf, tiles + t0, k, nullptr, nullptr, hp->comp, dstats, eos);
+        rc = custom ? (*custom)(n, fabs.data(), tiles + t0, hp->comp)
+                    : launch(path, n, fabs.data(), nf, tiles + t0, k, nullptr, nullptr, hp->comp, dstats, eos);
         if (rc != HC_OK) break;
         CUDA_TRY(cudaEventRecord(e_k, hp->comp));
         CUDA_TRY(cudaStreamWaitEvent(hp->d2h, e_k, 0));
@@ -784,6 +791,116 @@ int run_host(int path, int ntiles, std::vector<HostSlot>& slots, const HcBox* ti
     CUDA_TRY(cudaStreamSynchronize(hp->d2h));
     for (cudaEvent_t e : events) cudaEventDestroy(e);
     return rc;
+}
+
+
+// ---- update_state_with_sources / enforce_minimum_density / MultiFab component operations ----------------------------
+bool valid_src_params(const HcSrcParams* p) {
+    return p && p->gamma_minus_1 > 0.0 && p->h_species > 0.0 && p->h_species <= 1.0;
+}
+
+// tile descriptors of `nf` FAB slots in stream-ordered scratch: [256 B header][tiles]; returns the number of cells
+int stage_tiles(int ntiles, const HcFab* const* fabs, int nf, const HcBox* tiles, cudaStream_t stream, char*& scratch, int& n_used, long long& ncells) {
+    std::vector<TileDesc> h_tiles; h_tiles.reserve(ntiles);
+    ncells = 0; long long nchunks = 0;
+    for (int t = 0; t < ntiles; ++t) {
+        TileDesc td = make_tile(fabs, nf, t, tiles[t], ncells, nchunks);
+        if (td.nx <= 0 || td.ny <= 0 || td.nz <= 0) continue;
+        if (!tile_inside(td, nf)) { set_err("tile %d is not contained in its FABs (or a FAB pointer is null)", t); return HC_ERR_ARG; }
+        ncells += (long long)td.nx * td.ny * td.nz;
+        nchunks += (long long)td.cpr * td.ny * td.nz;
+        h_tiles.push_back(td);
+    }
+    n_used = (int)h_tiles.size();
+    scratch = nullptr;
+    if (ncells == 0) return HC_OK;
+    const size_t tiles_bytes = h_tiles.size() * sizeof(TileDesc);
+    CUDA_TRY(cudaMallocAsync((void**)&scratch, 256 + tiles_bytes, stream));
+    CUDA_TRY(cudaMemsetAsync(scratch, 0xff, 256, stream));     // the minimum key starts at its largest value
+    CUDA_TRY(cudaMemcpyAsync(scratch + 256, h_tiles.data(), tiles_bytes, cudaMemcpyHostToDevice, stream));
+    return HC_OK;
+}
+
+SrcArgs make_src_args(double dt, double a_old, double a_new, const HcSrcParams& p) {
+    SrcArgs a{};
+    // the scalars of Nyx_update_state_with_sources.cpp:25-31, same expressions
+    a.dt = dt; a.a_old = a_old;
+    a.a_half = 0.5 * (a_old + a_new);
+    a.a_half_inv = 1 / a.a_half;
+    a.a_oldsq = a_old * a_old;
+    a.a_newsq = a_new * a_new;
+    a.a_new_inv = 1.0 / a_new;
+    a.a_newsq_inv = 1.0 / a.a_newsq;
+    a.dt_a_new = dt / a_new;
+    a.a_half_dt = a.a_half * dt;
+    a.dt_a_half = dt * a.a_half;
+    a.small_dens = p.small_dens;
+    // floor_density: e from nyx_eos_given_RT(small_temp, Ne = 0) (eos_hc.H:222-231), (rho e) = small_dens * e
+    const double YHELIUM = (1.0 - p.h_species) / (4.0 * p.h_species);
+    const double mu = (1.0 + 4.0 * YHELIUM) / (1.0 + YHELIUM + 0.0);
+    const double eint_new = p.small_temp / (p.gamma_minus_1 * mp_over_kb * mu);
+    a.floor_rhoe = p.small_dens * eint_new;
+    a.sdc = p.sdc;
+    return a;
+}
+
+// mode 0: sweep (1)+(3) and the minimum, then the enforce kernel predicated on this call's own minimum (single rank);
+// mode 1: sweep (1)+(3) and the minimum accumulated into ext_min (device, caller-owned), no enforce kernel;
+// mode 2: the enforce kernel unconditionally (the caller has reduced the minimum over ranks / groups)
+int launch_sources(int mode, int ntiles, const HcFab* const* fabs, const HcBox* tiles, double dt, double a_old, double a_new, const HcSrcParams& p,
+                   double* min_dens_out, unsigned long long* ext_min, cudaStream_t stream) {
+    int dev; if (int rc = current_device(dev)) return rc;
+    int sms = 0; CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    char* scratch; int n_used; long long ncells;
+    if (int rc = stage_tiles(ntiles, fabs, 5, tiles, stream, scratch, n_used, ncells)) return rc;
+    if (min_dens_out) *min_dens_out = DBL_MAX;
+    if (ncells == 0) return HC_OK;
+    SrcArgs a = make_src_args(dt, a_old, a_new, p);
+    a.tiles = reinterpret_cast<const TileDesc*>(scratch + 256);
+    a.ntiles = n_used; a.ncells = ncells;
+    a.min_key = ext_min ? ext_min : reinterpret_cast<unsigned long long*>(scratch);
+    const long long per_cta = SRC_THREADS * SRC_U;
+    const int grid = (int)std::min<long long>((ncells + per_cta - 1) / per_cta, (long long)sms * 8);
+    if (mode != 2) hc_sources_kernel<false><<<grid, SRC_THREADS, 0, stream>>>(a);
+    if (mode == 0) { a.use_flag = 1; hc_sources_kernel<true><<<grid, SRC_THREADS, 0, stream>>>(a); }
+    if (mode == 2) { a.use_flag = 0; hc_sources_kernel<true><<<grid, SRC_THREADS, 0, stream>>>(a); }
+    CUDA_TRY(cudaGetLastError());
+    if (min_dens_out && mode != 2) {
+        unsigned long long key = 0;
+        CUDA_TRY(cudaMemcpyAsync(&key, a.min_key, sizeof key, cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        *min_dens_out = dens_from_key(key);
+    }
+    CUDA_TRY(cudaFreeAsync(scratch, stream));
+    return HC_OK;
+}
+
+int check_src_fabs(int ntiles, const HcFab* s_old, const HcFab* s_new, const HcFab* ext, const HcFab* hs, const HcFab* grav) {
+    for (int t = 0; t < ntiles; ++t) {
+        if (s_old[t].ncomp != 6 || s_new[t].ncomp != 6 || ext[t].ncomp != 6 || hs[t].ncomp != 6 || grav[t].ncomp < 3) {
+            set_err("tile %d: state, source FABs need 6 components (CONST_SPECIES build of the reference), grav_vector 3", t); return HC_ERR_ARG;
+        }
+    }
+    return HC_OK;
+}
+
+int launch_fab_op(int op, int ntiles, const HcFab* dst, int dcomp, const HcFab* src, int scomp, int ncomp, const HcBox* tiles, cudaStream_t stream) {
+    int dev; if (int rc = current_device(dev)) return rc;
+    int sms = 0; CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    for (int t = 0; t < ntiles; ++t)
+        if (dcomp < 0 || scomp < 0 || ncomp < 0 || dcomp + ncomp > dst[t].ncomp || scomp + ncomp > src[t].ncomp) { set_err("component range outside FAB %d", t); return HC_ERR_ARG; }
+    const HcFab* fabs[2] = {dst, src};
+    char* scratch; int n_used; long long ncells;
+    if (int rc = stage_tiles(ntiles, fabs, 2, tiles, stream, scratch, n_used, ncells)) return rc;
+    if (ncells == 0 || ncomp == 0) { if (scratch) CUDA_TRY(cudaFreeAsync(scratch, stream)); return HC_OK; }
+    FabOpArgs a{};
+    a.tiles = reinterpret_cast<const TileDesc*>(scratch + 256);
+    a.ntiles = n_used; a.ncells = ncells; a.scomp = scomp; a.dcomp = dcomp; a.ncomp = ncomp; a.op = op;
+    const int grid = (int)std::min<long long>((ncells + 255) / 256, (long long)sms * 16);
+    hc_fab_op_kernel<<<grid, 256, 0, stream>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaFreeAsync(scratch, stream));
+    return HC_OK;
 }
 
 }  // namespace
@@ -928,7 +1045,7 @@ int hc_integrate_struct_host(int ntiles, const HcFab* s_old, const HcFab* diag, 
         {s_new, {DENS, EDEN, EINT}, src ? std::vector<int>{EDEN, EINT} : std::vector<int>{}},
         {hydro_src, {DENS, EINT}, {}},
         {reset_src, {0}, {}},
-        {ir, {}, src ? std::vector<int>{0} : std::vector<int>{}}};
+        {ir, src ? std::vector<int>{0} : std::vector<int>{}, src ? std::vector<int>{0} : std::vector<int>{}}};   // in as well: whole components travel back, the ghost cells must keep their values
     return run_host(PATH_STRUCT, ntiles, slots, tiles, k, stats);
 }
 
@@ -951,6 +1068,101 @@ int hc_reset_internal_energy_host(int ntiles, const HcFab* state, const HcFab* d
     EosOpts eos; eos.small_temp = small_temp; eos.interp = interp;
     std::vector<HostSlot> slots = {{state, {0, 1, 2, 3, EDEN, EINT}, {EDEN, EINT}}, {diag, {NE}, {}}, {reset_src, {0}, {0}}};
     return run_host(PATH_RESET_E, ntiles, slots, tiles, k, nullptr, &eos);
+}
+
+void hc_default_src_params(HcSrcParams* p) {
+    if (!p) return;
+    p->small_dens = -1.e200; p->small_temp = -1.e200;   // Source/Driver/Nyx.cpp:98-99
+    p->gamma_minus_1 = 5.0 / 3.0 - 1.0; p->h_species = 0.76;
+    p->min_density_type = HC_MIN_DENSITY_FLOOR; p->sdc = 1;
+}
+
+#define HC_SRC_CHECK() \
+    if (ntiles < 0 || (ntiles > 0 && (!s_old || !s_new || !ext_src_old || !hydro_src || !grav || !tiles)) || !valid_src_params(prm) || !(a_old > 0.0) || \
+        !(a_new > 0.0)) { set_err("bad argument"); return HC_ERR_ARG; } \
+    if (prm->min_density_type != HC_MIN_DENSITY_FLOOR) { \
+        set_err("enforce_min_density_type = conservative exchanges density with neighbour cells through the host framework's FillPatch; only floor is on this path"); \
+        return HC_ERR_ARG; } \
+    if (int rc = check_src_fabs(ntiles, s_old, s_new, ext_src_old, hydro_src, grav)) return rc;
+
+int hc_update_state_with_sources_batch(int ntiles, const HcFab* s_old, const HcFab* s_new, const HcFab* ext_src_old, const HcFab* hydro_src,
+                                       const HcFab* grav, const HcBox* tiles, double dt, double a_old, double a_new, const HcSrcParams* prm,
+                                       double* min_dens, void* stream) {
+    HC_SRC_CHECK();
+    const HcFab* fabs[5] = {s_old, s_new, ext_src_old, hydro_src, grav};
+    return launch_sources(0, ntiles, fabs, tiles, dt, a_old, a_new, *prm, min_dens, nullptr, (cudaStream_t)stream);
+}
+
+int hc_enforce_minimum_density_batch(int ntiles, const HcFab* s_old, const HcFab* s_new, const HcFab* ext_src_old, const HcFab* hydro_src,
+                                     const HcFab* grav, const HcBox* tiles, double dt, double a_old, double a_new, const HcSrcParams* prm,
+                                     void* stream) {
+    HC_SRC_CHECK();
+    const HcFab* fabs[5] = {s_old, s_new, ext_src_old, hydro_src, grav};
+    return launch_sources(2, ntiles, fabs, tiles, dt, a_old, a_new, *prm, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+int hc_enforce_minimum_density_host(int ntiles, const HcFab* s_old, const HcFab* s_new, const HcFab* ext_src_old, const HcFab* hydro_src,
+                                    const HcFab* grav, const HcBox* tiles, double dt, double a_old, double a_new, const HcSrcParams* prm) {
+    HC_SRC_CHECK();
+    if (ntiles == 0) return HC_OK;
+    // every cell again from the untouched inputs with the floor in between; hydro_src(rho) goes back as well
+    // (S_new travels in too: whole components travel back, and its ghost cells must keep their values)
+    const std::vector<int> all6 = {0, 1, 2, 3, 4, 5};
+    const HcSrcParams p = *prm;
+    std::vector<HostSlot> slots2 = {{s_old, all6, {}}, {s_new, all6, all6}, {ext_src_old, all6, {}},
+                                    {hydro_src, all6, p.sdc ? std::vector<int>{0} : std::vector<int>{}}, {grav, {0, 1, 2}, {}}};
+    GroupLauncher pass2 = [&](int n, const HcFab* const* fabs, const HcBox* tl, cudaStream_t st) {
+        return launch_sources(2, n, fabs, tl, dt, a_old, a_new, p, nullptr, nullptr, st);
+    };
+    return run_host(-1, ntiles, slots2, tiles, Consts{}, nullptr, nullptr, &pass2);
+}
+
+int hc_update_state_with_sources_host(int ntiles, const HcFab* s_old, const HcFab* s_new, const HcFab* ext_src_old, const HcFab* hydro_src,
+                                      const HcFab* grav, const HcBox* tiles, double dt, double a_old, double a_new, const HcSrcParams* prm,
+                                      double* min_dens) {
+    HC_SRC_CHECK();
+    if (min_dens) *min_dens = DBL_MAX;
+    if (ntiles == 0) return HC_OK;
+    int dev; if (int rc = current_device(dev)) return rc;
+    HostPipe* hp = nullptr;
+    if (int rc = host_pipe(dev, hp)) return rc;
+    unsigned long long* dmin = nullptr;
+    CUDA_TRY(cudaMallocAsync((void**)&dmin, 8, hp->comp));
+    CUDA_TRY(cudaMemsetAsync(dmin, 0xff, 8, hp->comp));
+    const std::vector<int> all6 = {0, 1, 2, 3, 4, 5};
+    // pass 1: sweeps (1)+(3) per group of tiles, the minimum accumulated over the groups on the device
+    std::vector<HostSlot> slots = {{s_old, all6, {}}, {s_new, all6, all6}, {ext_src_old, all6, {}}, {hydro_src, all6, {}}, {grav, {0, 1, 2}, {}}};
+    // (S_new travels in as well: whole components travel back, and its ghost cells must keep their values)
+    const HcSrcParams p = *prm;
+    GroupLauncher pass1 = [&](int n, const HcFab* const* fabs, const HcBox* tl, cudaStream_t st) {
+        return launch_sources(1, n, fabs, tl, dt, a_old, a_new, p, nullptr, dmin, st);
+    };
+    int rc = run_host(-1, ntiles, slots, tiles, Consts{}, nullptr, nullptr, &pass1);
+    unsigned long long key = ~0ull;
+    if (rc == HC_OK) {
+        CUDA_TRY(cudaMemcpyAsync(&key, dmin, 8, cudaMemcpyDeviceToHost, hp->comp));
+        CUDA_TRY(cudaStreamSynchronize(hp->comp));
+    }
+    CUDA_TRY(cudaFreeAsync(dmin, hp->comp));
+    if (rc != HC_OK) return rc;
+    const double m = dens_from_key(key);
+    if (min_dens) *min_dens = m;
+    if (m < p.small_dens)   // pass 2 (rare)
+        rc = hc_enforce_minimum_density_host(ntiles, s_old, s_new, ext_src_old, hydro_src, grav, tiles, dt, a_old, a_new, prm);
+    return rc;
+}
+
+int hc_fab_copy_batch(int ntiles, const HcFab* dst, int dcomp, const HcFab* src, int scomp, int ncomp, const HcBox* tiles, void* stream) {
+    if (ntiles < 0 || (ntiles > 0 && (!dst || !src || !tiles))) { set_err("bad argument"); return HC_ERR_ARG; }
+    return launch_fab_op(0, ntiles, dst, dcomp, src, scomp, ncomp, tiles, (cudaStream_t)stream);
+}
+int hc_fab_add_batch(int ntiles, const HcFab* dst, int dcomp, const HcFab* src, int scomp, int ncomp, const HcBox* tiles, void* stream) {
+    if (ntiles < 0 || (ntiles > 0 && (!dst || !src || !tiles))) { set_err("bad argument"); return HC_ERR_ARG; }
+    return launch_fab_op(1, ntiles, dst, dcomp, src, scomp, ncomp, tiles, (cudaStream_t)stream);
+}
+int hc_fab_subtract_batch(int ntiles, const HcFab* dst, int dcomp, const HcFab* src, int scomp, int ncomp, const HcBox* tiles, void* stream) {
+    if (ntiles < 0 || (ntiles > 0 && (!dst || !src || !tiles))) { set_err("bad argument"); return HC_ERR_ARG; }
+    return launch_fab_op(2, ntiles, dst, dcomp, src, scomp, ncomp, tiles, (cudaStream_t)stream);
 }
 
 int hc_measure_fp64_peak(double* flops_per_s) {

@@ -1,0 +1,102 @@
+// nyx_sources_dropin.cpp -- host side of SURVEY section 8f rank 2: the definition of
+//
+//     Nyx::update_state_with_sources
+//
+// with the reference's exact signature (Source/Driver/Nyx.H, SDC and non-SDC builds).  This translation unit REPLACES
+// Source/TimeStep/Nyx_update_state_with_sources.cpp in a Nyx build; its caller (Source/Hydro/sdc_hydro.cpp:100-106, strang_hydro.cpp)
+// compiles unchanged.  The reference makes three sweeps over the level with Nyx::enforce_minimum_density in the middle; here the MFIter
+// loop only COLLECTS Array4 views and one C-ABI call (include/nyx_hc.h: hc_update_state_with_sources_batch) does the source update, the
+// density floor and the gravity update of all local boxes in one fused streaming kernel.
+//
+// Differences a maintainer should know:
+//   * nyx.enforce_min_density_type = "floor" (the default, Source/Driver/Nyx.cpp:199) is on this path.  "conservative" exchanges density
+//     with neighbour cells through FillPatch and stays with the reference's translation unit: this file aborts on it;
+//   * the decision "is any new density below small_dens" is the reference's global S_new.min(): the local minimum comes back from the
+//     kernel, is reduced with ParallelDescriptor::ReduceRealMin, and a rank whose own boxes were fine but whose neighbours' were not
+//     runs the enforce kernel afterwards (it also rewrites hydro_src(rho) in every cell, as the reference does);
+//   * CONST_SPECIES builds (6 state components) only.
+#include <AMReX_MultiFab.H>
+#include <AMReX_ParallelDescriptor.H>
+#include <Nyx.H>
+
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "nyx_hc.h"
+
+using namespace amrex;
+
+namespace {
+HcFab src_fab(Array4<Real> const& a) {
+    HcFab f{};
+    f.p = a.p;
+    f.jstride = a.jstride; f.kstride = a.kstride; f.nstride = a.nstride;
+    f.lo[0] = a.begin.x; f.lo[1] = a.begin.y; f.lo[2] = a.begin.z;
+    f.hi[0] = a.end.x - 1; f.hi[1] = a.end.y - 1; f.hi[2] = a.end.z - 1;
+    f.ncomp = a.ncomp;
+    return f;
+}
+void src_check(int rc) {
+    if (rc != HC_OK) amrex::Abort(std::string("nyx_hc: ") + hc_last_error());
+}
+}  // namespace
+
+void
+Nyx::update_state_with_sources( MultiFab& S_old, MultiFab& S_new,
+                                MultiFab& ext_src_old, MultiFab& hydro_source,
+                                MultiFab& grav_vector,
+#ifdef SDC
+                                MultiFab& /* reset_e_src: only the conservative variant writes it */,
+#endif
+                                amrex::Real dt, amrex::Real a_old, amrex::Real a_new)
+{
+    BL_PROFILE("Nyx::update_state_with_sources()");
+    if (verbose)
+      amrex::Print() << "Updating state with the hydro sources ... " << std::endl;
+    if (enforce_min_density_type != "floor")
+        amrex::Abort("nyx_hc: enforce_min_density_type = " + enforce_min_density_type + " is not on the B200 path (only floor); link the reference's Nyx_update_state_with_sources.cpp instead");
+
+    HcSrcParams p;
+    hc_default_src_params(&p);
+    p.small_dens = small_dens;
+    p.small_temp = small_temp;
+    p.gamma_minus_1 = gamma - 1.0;
+    p.h_species = h_species;
+#ifdef SDC
+    p.sdc = 1;
+#else
+    p.sdc = 0;
+#endif
+
+    std::vector<HcFab> f[5]; std::vector<HcBox> t;
+    for (MFIter mfi(S_new); mfi.isValid(); ++mfi) {
+        f[0].push_back(src_fab(S_old.array(mfi))); f[1].push_back(src_fab(S_new.array(mfi))); f[2].push_back(src_fab(ext_src_old.array(mfi)));
+        f[3].push_back(src_fab(hydro_source.array(mfi))); f[4].push_back(src_fab(grav_vector.array(mfi)));
+        const Box& b = mfi.validbox();
+        HcBox hb;
+        for (int d = 0; d < 3; ++d) { hb.lo[d] = b.smallEnd(d); hb.hi[d] = b.bigEnd(d); }
+        t.push_back(hb);
+    }
+    const int n = (int)t.size();
+    Real local_min = std::numeric_limits<Real>::max();
+#ifdef AMREX_USE_GPU
+    src_check(hc_update_state_with_sources_batch(n, f[0].data(), f[1].data(), f[2].data(), f[3].data(), f[4].data(), t.data(), dt, a_old, a_new, &p,
+                                                 &local_min, nullptr));
+#else
+    src_check(hc_update_state_with_sources_host(n, f[0].data(), f[1].data(), f[2].data(), f[3].data(), f[4].data(), t.data(), dt, a_old, a_new, &p,
+                                                &local_min));
+#endif
+    // S_new.min(Density_comp) of the reference is a reduction over all ranks (Nyx_enforce_minimum_density.cpp:22)
+    Real global_min = local_min;
+    ParallelDescriptor::ReduceRealMin(global_min);
+    if (global_min < small_dens && !(local_min < small_dens) && n > 0) {
+#ifdef AMREX_USE_GPU
+        src_check(hc_enforce_minimum_density_batch(n, f[0].data(), f[1].data(), f[2].data(), f[3].data(), f[4].data(), t.data(), dt, a_old, a_new, &p,
+                                                   nullptr));
+        src_check(hc_sync(nullptr));
+#else
+        src_check(hc_enforce_minimum_density_host(n, f[0].data(), f[1].data(), f[2].data(), f[3].data(), f[4].data(), t.data(), dt, a_old, a_new, &p));
+#endif
+    }
+}

@@ -1168,3 +1168,78 @@ int hco_reset_internal_e_box(const hco_params* p, const hco_fab* u, const hco_fa
     }
     return 0;
 }
+
+/* ---- SDC source assembly.
+ * Nyx::update_state_with_sources (Source/TimeStep/Nyx_update_state_with_sources.cpp:9-121) is three sweeps: (1) the source update of
+ * every state component (:33-76), (2) Nyx::enforce_minimum_density over the whole MultiFab (Nyx_enforce_minimum_density.cpp:8-65, floor
+ * variant :67-107 with floor_density, Nyx_enforce_minimum_density.H:8-58) -- taken only when the minimum of the NEW density over all boxes
+ * is below small_dens, and then it also resets hydro_src(rho) in EVERY cell -- and (3) the gravity update (:92-120).  The minimum is
+ * global, so the port has one function per side of it. */
+
+/* sweep (1) over one box; returns the minimum of the new density over the box */
+double hco_sources_apply_box(const hco_fab* uin, const hco_fab* uout, const hco_fab* src, const hco_fab* hsrc, const int lo[3], const int hi[3],
+                             double dt, double a_old, double a_new) {
+    const double a_half = 0.5 * (a_old + a_new);
+    const double a_half_inv = 1 / a_half;
+    const double a_oldsq = a_old * a_old;
+    const double a_newsq = a_new * a_new;
+    const double a_new_inv = 1.0 / a_new;
+    const double a_newsq_inv = 1.0 / a_newsq;
+    double m = DBL_MAX;
+    for (int k = lo[2]; k <= hi[2]; ++k) for (int j = lo[1]; j <= hi[1]; ++j) for (int i = lo[0]; i <= hi[0]; ++i) {
+        for (int n = 0; n < uout->ncomp; ++n) {
+            double* o = at(uout, i, j, k, n);
+            if (n == DENS) {
+                *o = *at(uin, i, j, k, n) + *at(hsrc, i, j, k, n) + dt * *at(src, i, j, k, n) * a_half_inv;
+            } else if (n >= 1 && n <= 3) {
+                *o = a_old * *at(uin, i, j, k, n) + *at(hsrc, i, j, k, n) + dt * *at(src, i, j, k, n);
+                *o = *o * a_new_inv;
+            } else if (n == EDEN || n == EINT) {
+                *o = a_oldsq * *at(uin, i, j, k, n) + *at(hsrc, i, j, k, n) + a_half * dt * *at(src, i, j, k, n);
+                *o = *o * a_newsq_inv;
+            } else {
+                *o = *at(uin, i, j, k, n) + *at(hsrc, i, j, k, n) + dt * *at(src, i, j, k, n) * a_half_inv;
+            }
+        }
+        if (*at(uout, i, j, k, DENS) < m) m = *at(uout, i, j, k, DENS);
+    }
+    return m;
+}
+
+/* sweeps (2) -- only when enforce != 0, i.e. the caller found min over all boxes < small_dens -- and (3) over one box; sdc != 0: the
+ * reference's SDC build, which resets hydro_src(rho) */
+int hco_sources_finish_box(const hco_params* p, const hco_fab* uin, const hco_fab* uout, const hco_fab* hsrc, const hco_fab* grav,
+                           const int lo[3], const int hi[3], double dt, double a_old, double a_new, double small_dens, double small_temp,
+                           int enforce, int sdc) {
+    const double a_half = 0.5 * (a_old + a_new);
+    const double a_newsq = a_new * a_new;
+    const double a_newsq_inv = 1.0 / a_newsq;
+    const double dt_a_new = dt / a_new;
+    if (enforce) {
+        for (int k = lo[2]; k <= hi[2]; ++k) for (int j = lo[1]; j <= hi[1]; ++j) for (int i = lo[0]; i <= hi[0]; ++i) {
+            if (*at(uout, i, j, k, DENS) < small_dens) {   /* floor_density */
+                *at(uout, i, j, k, DENS) = small_dens;
+                *at(uout, i, j, k, 1) = 0.0; *at(uout, i, j, k, 2) = 0.0; *at(uout, i, j, k, 3) = 0.0;
+                const double eint_new = eos_e_given_T(p->gamma_minus_1, p->h_species, small_temp, 0.0);
+                *at(uout, i, j, k, EINT) = *at(uout, i, j, k, DENS) * eint_new;
+                *at(uout, i, j, k, EDEN) = *at(uout, i, j, k, EINT);
+            }
+        }
+        if (sdc)
+            for (int k = lo[2]; k <= hi[2]; ++k) for (int j = lo[1]; j <= hi[1]; ++j) for (int i = lo[0]; i <= hi[0]; ++i)
+                *at(hsrc, i, j, k, DENS) = *at(uout, i, j, k, DENS) - *at(uin, i, j, k, DENS);
+    }
+    for (int k = lo[2]; k <= hi[2]; ++k) for (int j = lo[1]; j <= hi[1]; ++j) for (int i = lo[0]; i <= hi[0]; ++i) {
+        const double rho = *at(uin, i, j, k, DENS);
+        const double SrU = rho * *at(grav, i, j, k, 0);
+        const double SrV = rho * *at(grav, i, j, k, 1);
+        const double SrW = rho * *at(grav, i, j, k, 2);
+        *at(uout, i, j, k, 1) += SrU * dt_a_new;
+        *at(uout, i, j, k, 2) += SrV * dt_a_new;
+        *at(uout, i, j, k, 3) += SrW * dt_a_new;
+        const double SrE = *at(uin, i, j, k, 1) * *at(grav, i, j, k, 0) + *at(uin, i, j, k, 2) * *at(grav, i, j, k, 1) +
+                           *at(uin, i, j, k, 3) * *at(grav, i, j, k, 2);
+        *at(uout, i, j, k, EDEN) = (a_newsq * *at(uout, i, j, k, EDEN) + SrE * (dt * a_half)) * a_newsq_inv;
+    }
+    return 0;
+}

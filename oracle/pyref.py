@@ -126,6 +126,16 @@ class Reference:
         self.lib.nyxref_reset_internal_energy(bp, ng_state, ng_diag, diag.shape[0], ng_reset, state.ctypes.data_as(_dp), diag.ctypes.data_as(_dp),
                                               reset_src.ctypes.data_as(_dp), a, small_temp, interp)
 
+    def update_state_with_sources(self, boxes, s_old, s_new, ext_src, hydro_src, grav, reset_src, dt, a_old, a_new, small_dens, small_temp,
+                                  ng=(0, 0, 0, 0, 0, 0)):
+        """Nyx::update_state_with_sources (SDC signature): the reference's own Nyx_update_state_with_sources.cpp over a multi-box MultiFab;
+        enforce_minimum_density (floor variant) restated around the reference's floor_density, see ref_driver.cpp"""
+        b, bp = self._boxes(boxes)
+        ngarr = (C.c_int * 6)(*ng)
+        self.lib.nyxref_update_state_with_sources.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)] + [_dpp] * 6 + [C.c_double] * 5
+        self.lib.nyxref_update_state_with_sources(len(b), bp, ngarr, _ptrs(s_old), _ptrs(s_new), _ptrs(ext_src), _ptrs(hydro_src), _ptrs(grav),
+                                                  _ptrs(reset_src), dt, a_old, a_new, small_dens, small_temp)
+
     def ion_n(self, JH, JHe, U, nh, ne, gm1, hsp, z):
         out = np.zeros(4)
         self.lib.nyxref_ion_n(JH, JHe, U, nh, ne, gm1, hsp, z, out.ctypes.data_as(_dp))
@@ -262,6 +272,30 @@ class Port:
         self.lib.hco_reset_internal_e_box.argtypes = [C.POINTER(HcoParams), C.POINTER(type(sf)), C.POINTER(type(sf)), C.POINTER(type(sf)), type(l), type(l),
                                                       C.c_double, C.c_int]
         self.lib.hco_reset_internal_e_box(C.byref(p), C.byref(sf), C.byref(df), C.byref(rf), l, h, small_temp, interp)
+
+    def update_state_with_sources(self, boxes, s_old, s_new, ext_src, hydro_src, grav, dt, a_old, a_new, small_dens, small_temp,
+                                  ng=(0, 0, 0, 0, 0), sdc=1, params=None, global_min=None):
+        """lists of per-box arrays (ncomp, nz, ny, nx), each covering its box grown by ng[slot]; slots: s_old, s_new, ext_src, hydro_src, grav.
+        Returns the minimum of the new density over all boxes (before the floor); global_min overrides it for the decision (multi-rank)."""
+        p = params or self.params()
+        lib = self.lib
+        fp = C.POINTER(HcoFab)
+        l3 = C.c_int * 3
+        lib.hco_sources_apply_box.restype = C.c_double
+        lib.hco_sources_apply_box.argtypes = [fp] * 4 + [l3, l3, C.c_double, C.c_double, C.c_double]
+        lib.hco_sources_finish_box.argtypes = [C.POINTER(HcoParams)] + [fp] * 4 + [l3, l3] + [C.c_double] * 5 + [C.c_int, C.c_int]
+        fabs = []
+        for bi, bx in enumerate(boxes):
+            lo, hi = tuple(bx[:3]), tuple(bx[3:])
+            f = [fab_of(arrs[bi], tuple(x - g for x in lo)) for arrs, g in zip((s_old, s_new, ext_src, hydro_src, grav), ng)]
+            fabs.append((f, l3(*lo), l3(*hi)))
+        m = min(lib.hco_sources_apply_box(C.byref(f[0]), C.byref(f[1]), C.byref(f[2]), C.byref(f[3]), lo, hi, dt, a_old, a_new)
+                for f, lo, hi in fabs)
+        decide = m if global_min is None else global_min
+        for f, lo, hi in fabs:
+            lib.hco_sources_finish_box(C.byref(p), C.byref(f[0]), C.byref(f[1]), C.byref(f[3]), C.byref(f[4]), lo, hi, dt, a_old, a_new,
+                                       small_dens, small_temp, int(decide < small_dens), sdc)
+        return m
 
     def eos_box(self, state, diag, lo, hi, a, params=None):
         p = params or self.params()

@@ -256,3 +256,70 @@ void nyxref_compute_new_temp(const int* box, int ng_state, int ng_diag, int ncom
     }
 }
 }
+
+// ---- the SDC source assembly either side of sdc_reactions.
+// Nyx::update_state_with_sources is the reference's own translation unit Source/TimeStep/Nyx_update_state_with_sources.cpp, compiled
+// unmodified (with -DSDC) by oracle/Makefile.  It calls Nyx::enforce_minimum_density, whose file (Nyx_enforce_minimum_density.cpp) also
+// holds the "conservative" variant that needs AMReX's FillPatch and cannot be built here: the top-level function (:8-65) and the floor
+// variant (:67-107) are RESTATED below around the reference's own per-cell function floor_density (Nyx_enforce_minimum_density.H:8-58).
+#include <Nyx_enforce_minimum_density.H>
+Real Nyx::small_dens = -1.e200;   // Source/Driver/Nyx.cpp:98-99,199
+Real Nyx::small_temp = -1.e200;
+std::string Nyx::enforce_min_density_type = "floor";
+
+void Nyx::enforce_minimum_density(MultiFab& S_old, MultiFab& S_new, MultiFab& hydro_source, MultiFab& reset_e_src, Real a_new) {
+    if (S_new.min(Density_comp) < small_dens) {
+        if (enforce_min_density_type == "floor") {
+            enforce_minimum_density_floor(S_new, a_new);
+        } else if (enforce_min_density_type == "conservative") {
+            amrex::Abort("oracle/_ref: the conservative variant needs FillPatch (AMReX) and is not built");
+        } else {
+            amrex::Abort("Don't know this enforce_min_density_type");
+        }
+        for (MFIter mfi(hydro_source, TilingIfNotGPU()); mfi.isValid(); ++mfi) {
+            const Box& bx = mfi.tilebox();
+            auto const& hydro_src = hydro_source.array(mfi);
+            auto const& uin = S_old.array(mfi);
+            auto const& uout = S_new.array(mfi);
+            amrex::ParallelFor(bx, [=](int i, int j, int k) noexcept {
+                hydro_src(i,j,k,Density_comp) = uout(i,j,k,Density_comp) - uin(i,j,k,Density_comp);
+            });
+        }
+    }
+}
+
+void Nyx::enforce_minimum_density_floor(MultiFab& S_new, Real a_new_in) {
+    Real lsmall_dens = small_dens;
+    Real lgamma_minus_1 = gamma - 1.0;
+    Real lsmall_temp = small_temp;
+    auto atomic_rates = atomic_rates_glob;
+    Real l_h_species = h_species;
+    for (MFIter mfi(S_new, TilingIfNotGPU()); mfi.isValid(); ++mfi) {
+        const Box& bx = mfi.tilebox();
+        auto const& uout = S_new.array(mfi);
+        amrex::ParallelFor(bx, [=](int i, int j, int k) noexcept {
+            floor_density(i, j, k, uout, atomic_rates, a_new_in, lgamma_minus_1, lsmall_dens, lsmall_temp, l_h_species);
+        });
+    }
+}
+
+extern "C" {
+// ng[6] / pointers in the reference's argument order: S_old, S_new, ext_src_old, hydro_source, grav_vector, reset_e_src
+// (6, 6, 6, 6, 3, 1 components)
+void nyxref_update_state_with_sources(int nboxes, const int* boxes, const int* ng, double* const* s_old, double* const* s_new,
+                                      double* const* ext_src, double* const* hydro_src, double* const* grav, double* const* reset_src,
+                                      double dt, double a_old, double a_new, double small_dens, double small_temp) {
+    BoxArray ba = make_ba(nboxes, boxes);
+    MultiFab S_old, S_new, E, H, G, R;
+    S_old.defineAlias(ba, 6, ng[0], s_old);
+    S_new.defineAlias(ba, 6, ng[1], s_new);
+    E.defineAlias(ba, 6, ng[2], ext_src);
+    H.defineAlias(ba, 6, ng[3], hydro_src);
+    G.defineAlias(ba, 3, ng[4], grav);
+    R.defineAlias(ba, 1, ng[5], reset_src);
+    Nyx::small_dens = small_dens;
+    Nyx::small_temp = small_temp;
+    Nyx nyx;
+    nyx.update_state_with_sources(S_old, S_new, E, H, G, R, dt, a_old, a_new);
+}
+}

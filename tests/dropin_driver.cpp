@@ -29,6 +29,9 @@ IntVect Nyx::sundials_tile_size(1024000, 8, 8);
 int Nyx::inhomo_reion = 0;
 long int Nyx::old_max_sundials_steps = 3;
 long int Nyx::new_max_sundials_steps = 3;
+Real Nyx::small_dens = -1.e200;
+Real Nyx::small_temp = -1.e200;
+std::string Nyx::enforce_min_density_type = "floor";
 
 extern "C" const HcStats* nyx_hc_last_stats();
 void nyx_hc_compute_new_temp(MultiFab& S_new, MultiFab& D_new, Real a, Real small_temp, Real large_temp, int max_temp_dt);
@@ -111,6 +114,23 @@ void nyxref_reset_internal_energy(const int* box, int ng_state, int ng_diag, int
     D.defineAlias(ba, ncomp_diag, ng_diag, dp);
     R.defineAlias(ba, 1, ng_reset, rp);
     nyx_hc_reset_internal_energy(S, D, R, a, small_temp, interp);
+}
+
+void nyxref_update_state_with_sources(int nboxes, const int* boxes, const int* ng, double* const* s_old, double* const* s_new,
+                                      double* const* ext_src, double* const* hydro_src, double* const* grav, double* const* reset_src,
+                                      double dt, double a_old, double a_new, double small_dens, double small_temp) {
+    BoxArray ba = make_ba(nboxes, boxes);
+    MultiFab S_old, S_new, E, H, G, R;
+    S_old.defineAlias(ba, 6, ng[0], s_old);
+    S_new.defineAlias(ba, 6, ng[1], s_new);
+    E.defineAlias(ba, 6, ng[2], ext_src);
+    H.defineAlias(ba, 6, ng[3], hydro_src);
+    G.defineAlias(ba, 3, ng[4], grav);
+    R.defineAlias(ba, 1, ng[5], reset_src);
+    Nyx::small_dens = small_dens;
+    Nyx::small_temp = small_temp;
+    Nyx nyx;
+    nyx.update_state_with_sources(S_old, S_new, E, H, G, R, dt, a_old, a_new);
 }
 
 }  // extern "C"

@@ -513,3 +513,129 @@ def test_inhomogeneous_reionization_on_device(hc_lib, port):
     z_end = 1.0 / d["a_end"] - 1.0
     cold_during = (d["diag"][2] >= z_end) & (d["diag"][2] < z) & (d["diag"][0] < 5.0e3)
     assert cold_during.sum() > 50 and np.mean(out["s_new"][5][cold_during] > d["s_new"][5][cold_during]) > 0.95
+
+
+# ---------------------------------------------------------------------------------------------- SDC source assembly
+def _src_fabs(d, arrs, pinned_host=False):
+    """per slot the HcFab list over arrs[slot][box] (torch device tensors or numpy arrays), each covering its box grown by ng[slot]"""
+    fabs = {}
+    for slot, g in zip(("s_old", "s_new", "ext_src", "hydro_src", "grav", "reset_src"), d["ng"]):
+        mk = capi.fab_of_numpy if pinned_host else capi.fab_of_torch
+        fabs[slot] = [mk(arrs[slot][bi], tuple(x - g for x in bx[:3])) for bi, bx in enumerate(d["boxes"])]
+    tiles = [capi.make_box(bx[:3], bx[3:]) for bx in d["boxes"]]
+    return fabs, tiles
+
+
+def _src_oracle(port, d):
+    import copy
+    p = copy.deepcopy({k: d[k] for k in ("s_old", "s_new", "ext_src", "hydro_src", "grav")})
+    m = port.update_state_with_sources(d["boxes"], p["s_old"], p["s_new"], p["ext_src"], p["hydro_src"], p["grav"], d["dt"], d["a_old"],
+                                       d["a_new"], d["small_dens"], d["small_temp"], ng=d["ng"][:5])
+    return p, m
+
+
+@pytest.mark.parametrize("low", [0, 7])
+@pytest.mark.parametrize("host", [False, True])
+def test_update_state_with_sources_bitwise(hc_lib, port, low, host):
+    """Nyx::update_state_with_sources + enforce_minimum_density(floor) + gravity as one fused sweep: a ragged three-box level with the
+    production ghost widths, with and without cells below small_dens, device FABs and host FABs (pipelined entry point): every byte of
+    S_new (ghost cells included: untouched), hydro_src and the inputs equals the oracle's, and so does the reported minimum."""
+    torch = _torch()
+    d = util.sources_inputs(seed=900 + low, low_density_cells=low)
+    ref, m_ref = _src_oracle(port, d)
+    prm = hc_lib.src_params(small_dens=d["small_dens"], small_temp=d["small_temp"])
+    slots = ("s_old", "s_new", "ext_src", "hydro_src", "grav", "reset_src")
+    if host:
+        arrs = {k: [x.copy() for x in d[k]] for k in slots}
+        fabs, tiles = _src_fabs(d, arrs, pinned_host=True)
+    else:
+        arrs = {k: [torch.from_numpy(x).cuda() for x in d[k]] for k in slots}
+        fabs, tiles = _src_fabs(d, arrs)
+    m = hc_lib.update_state_with_sources_batch(fabs["s_old"], fabs["s_new"], fabs["ext_src"], fabs["hydro_src"], fabs["grav"], tiles, d["dt"],
+                                               d["a_old"], d["a_new"], prm, host=host)
+    assert m == m_ref and (m < d["small_dens"]) == (low > 0)
+    get = (lambda x: x) if host else (lambda x: x.cpu().numpy())
+    for bi in range(len(d["boxes"])):
+        for k in ("s_new", "hydro_src", "s_old", "ext_src", "grav"):
+            assert np.array_equal(get(arrs[k][bi]), ref[k][bi]), (k, bi)
+
+
+@pytest.mark.parametrize("host", [False, True])
+def test_enforce_minimum_density_multi_rank_protocol(hc_lib, port, host):
+    """Two 'ranks' (two disjoint tile sets): only rank 1 has cells below small_dens.  Each rank runs hc_update_state_with_sources_batch on
+    its own tiles, the minima are reduced (the reference's S_new.min() is global), and rank 0 -- whose own minimum was fine -- then calls
+    hc_enforce_minimum_density_batch.  The result equals the oracle run over all boxes at once, bit for bit."""
+    torch = _torch()
+    d = util.sources_inputs(seed=930, low_density_cells=5)
+    for bi in (0, 1):      # rank 0 = boxes 0, 1: take their low-density cells away again
+        d["hydro_src"][bi][0] = np.abs(d["hydro_src"][bi][0])
+    ref, m_ref = _src_oracle(port, d)
+    prm = hc_lib.src_params(small_dens=d["small_dens"], small_temp=d["small_temp"])
+    slots = ("s_old", "s_new", "ext_src", "hydro_src", "grav", "reset_src")
+    arrs = {k: [x.copy() if host else torch.from_numpy(x).cuda() for x in d[k]] for k in slots}
+    fabs, tiles = _src_fabs(d, arrs, pinned_host=host)
+    ranks = [[0, 1], [2]]
+    mins = []
+    for own in ranks:
+        sub = lambda k: [fabs[k][i] for i in own]
+        mins.append(hc_lib.update_state_with_sources_batch(sub("s_old"), sub("s_new"), sub("ext_src"), sub("hydro_src"), sub("grav"),
+                                                           [tiles[i] for i in own], d["dt"], d["a_old"], d["a_new"], prm, host=host))
+    assert mins[0] >= d["small_dens"] > mins[1] and min(mins) == m_ref
+    for own, m in zip(ranks, mins):
+        if min(mins) < d["small_dens"] and not (m < d["small_dens"]):
+            sub = lambda k: [fabs[k][i] for i in own]
+            hc_lib.enforce_minimum_density_batch(sub("s_old"), sub("s_new"), sub("ext_src"), sub("hydro_src"), sub("grav"), [tiles[i] for i in own],
+                                                 d["dt"], d["a_old"], d["a_new"], prm, host=host)
+    torch.cuda.synchronize()
+    for bi in range(len(d["boxes"])):
+        for k in ("s_new", "hydro_src"):
+            assert np.array_equal(arrs[k][bi] if host else arrs[k][bi].cpu().numpy(), ref[k][bi]), (k, bi)
+
+
+def test_sources_argument_errors_and_async(hc_lib):
+    """conservative variant and wrong component counts are rejected; want_min=False does not synchronise and gives the same S_new"""
+    torch = _torch()
+    d = util.sources_inputs(seed=940)
+    slots = ("s_old", "s_new", "ext_src", "hydro_src", "grav", "reset_src")
+    arrs = {k: [torch.from_numpy(x).cuda() for x in d[k]] for k in slots}
+    fabs, tiles = _src_fabs(d, arrs)
+    args = (fabs["s_old"], fabs["s_new"], fabs["ext_src"], fabs["hydro_src"], fabs["grav"], tiles, d["dt"], d["a_old"], d["a_new"])
+    with pytest.raises(capi.HcError, match="conservative"):
+        hc_lib.update_state_with_sources_batch(*args, hc_lib.src_params(small_dens=1.0, small_temp=1.0, min_density_type=1))
+    with pytest.raises(capi.HcError, match="6 components"):
+        hc_lib.update_state_with_sources_batch(fabs["s_old"], fabs["s_new"], fabs["ext_src"], fabs["hydro_src"], fabs["reset_src"], tiles, d["dt"], d["a_old"],
+                                               d["a_new"], hc_lib.src_params())
+    prm = hc_lib.src_params(small_dens=d["small_dens"], small_temp=d["small_temp"])
+    hc_lib.update_state_with_sources_batch(*args, prm)
+    first = [x.clone() for x in arrs["s_new"]]
+    assert hc_lib.update_state_with_sources_batch(*args, prm, want_min=False) is None
+    torch.cuda.synchronize()
+    assert all(torch.equal(x, y) for x, y in zip(first, arrs["s_new"]))
+    assert hc_lib.update_state_with_sources_batch([], [], [], [], [], [], d["dt"], d["a_old"], d["a_new"], prm) == np.finfo(np.float64).max
+
+
+def test_fab_copy_add_subtract(hc_lib):
+    """MultiFab::Copy / Add / Subtract of a component range over valid boxes (sdc_hydro.cpp:83-84,94-95,112,135), FABs with different ghost widths"""
+    torch = _torch()
+    rng = np.random.default_rng(950)
+    boxes = util.SRC_BOXES
+    shp = lambda bx, g: (bx[5] - bx[2] + 1 + 2 * g, bx[4] - bx[1] + 1 + 2 * g, bx[3] - bx[0] + 1 + 2 * g)
+    ext = [rng.standard_normal((6,) + shp(b, 4)) for b in boxes]
+    ir = [rng.standard_normal((1,) + shp(b, 1)) for b in boxes]
+    ext_d, ir_d = [torch.from_numpy(x).cuda() for x in ext], [torch.from_numpy(x).cuda() for x in ir]
+    fe = [capi.fab_of_torch(x, tuple(c - 4 for c in b[:3])) for x, b in zip(ext_d, boxes)]
+    fi = [capi.fab_of_torch(x, tuple(c - 1 for c in b[:3])) for x, b in zip(ir_d, boxes)]
+    tiles = [capi.make_box(b[:3], b[3:]) for b in boxes]
+    want = [x.copy() for x in ext]
+    v4, v1 = (slice(4, -4),) * 3, (slice(1, -1),) * 3
+    for op, comp in (("add", 4), ("add", 5), ("subtract", 4), ("copy", 1)):
+        hc_lib.fab_op_batch(op, fe, comp, fi, 0, 1, tiles)
+        for w, s in zip(want, ir):
+            if op == "add": w[(comp,) + v4] = w[(comp,) + v4] + s[(0,) + v1]
+            elif op == "subtract": w[(comp,) + v4] = w[(comp,) + v4] - s[(0,) + v1]
+            else: w[(comp,) + v4] = s[(0,) + v1]
+    torch.cuda.synchronize()
+    for x, w in zip(ext_d, want):
+        assert np.array_equal(x.cpu().numpy(), w)
+    with pytest.raises(capi.HcError, match="component range"):
+        hc_lib.fab_op_batch("copy", fe, 6, fi, 0, 1, tiles)

@@ -156,3 +156,32 @@ def test_inhomogeneous_reionization_bitwise(reference, port):
         assert np.array_equal(d[k], r[k]), k
     assert np.array_equal(reference.stats(), pst[:, :8])
     assert not np.array_equal(d["s_new"][5], util.inhomo_inputs(z, n, 331)["s_new"][5])
+
+
+@pytest.mark.parametrize("low", [0, 7])
+def test_update_state_with_sources_bitwise(reference, port, low):
+    """the reference's own Nyx_update_state_with_sources.cpp (+ floor_density) over a ragged three-box level with the
+    production ghost widths, against the port: every component of S_new and hydro_src bit for bit, with (low > 0) and without cells
+    below small_dens."""
+    import copy
+    d = util.sources_inputs(seed=811 + low, low_density_cells=low)
+    r = copy.deepcopy(d)
+    reference.update_state_with_sources(d["boxes"], r["s_old"], r["s_new"], r["ext_src"], r["hydro_src"], r["grav"], r["reset_src"],
+                                        d["dt"], d["a_old"], d["a_new"], d["small_dens"], d["small_temp"], ng=d["ng"])
+    p = copy.deepcopy(d)
+    m = port.update_state_with_sources(d["boxes"], p["s_old"], p["s_new"], p["ext_src"], p["hydro_src"], p["grav"], d["dt"], d["a_old"],
+                                       d["a_new"], d["small_dens"], d["small_temp"], ng=d["ng"][:5])
+    assert (m < d["small_dens"]) == (low > 0)
+    n_floor = 0
+    for bi in range(len(d["boxes"])):
+        v = (slice(None), slice(1, -1), slice(1, -1), slice(1, -1))       # valid region of S_new (one ghost cell)
+        assert np.array_equal(r["s_new"][bi][v], p["s_new"][bi][v])
+        assert np.array_equal(r["s_new"][bi], p["s_new"][bi])             # ghost cells untouched on both sides
+        assert np.array_equal(r["hydro_src"][bi], p["hydro_src"][bi])
+        assert np.array_equal(r["s_old"][bi], d["s_old"][bi]) and np.array_equal(p["s_old"][bi], d["s_old"][bi])
+        n_floor += int((p["s_new"][bi][0][v[1:]] == d["small_dens"]).sum())
+        if low:
+            assert not np.array_equal(p["hydro_src"][bi][0], d["hydro_src"][bi][0])     # reset in every cell
+        else:
+            assert np.array_equal(p["hydro_src"][bi][0], d["hydro_src"][bi][0])
+    assert (n_floor >= low) if low else n_floor == 0     # about 3/4 of the 3 x low prepared cells end below small_dens

@@ -68,6 +68,50 @@ def eos_rows_inputs(n, seed, z=3.0):
     return state, diag, reset_src
 
 
+SRC_BOXES = [(0, 0, 0, 15, 11, 9), (16, 0, 0, 27, 11, 9), (0, 12, 0, 27, 19, 9)]   # ragged: 16x12x10, 12x12x10, 28x8x10
+SRC_NG = (4, 1, 4, 0, 1, 4)     # S_old_tmp, S_new, ext_src_old, hydro_src, grav_vector, reset_e_src (sdc_hydro.cpp:60-106)
+SRC_NCOMP = (6, 6, 6, 6, 3, 1)
+
+
+def sources_inputs(seed, z=3.0, low_density_cells=0, boxes=SRC_BOXES, ng=SRC_NG):
+    """Inputs of Nyx::update_state_with_sources (SDC) on a multi-box level: per slot a list of per-box arrays (ncomp, nz, ny, nx) covering
+    the box grown by ng[slot].  low_density_cells > 0: that many cells per box get a hydro source that drives the new density below
+    small_dens (and a few exactly to it), so that enforce_minimum_density acts."""
+    rng = np.random.default_rng(seed)
+    a_old = 1.0 / (1.0 + z)
+    dt = synth.step_dt(z)
+    a_new = synth.a_after(z, dt)
+    small_dens = 1.0e-2 * synth.mean_rhob()
+    out = {k: [] for k in ("s_old", "s_new", "ext_src", "hydro_src", "grav", "reset_src")}
+    for bi, bx in enumerate(boxes):
+        shp = lambda g: (bx[5] - bx[2] + 1 + 2 * g, bx[4] - bx[1] + 1 + 2 * g, bx[3] - bx[0] + 1 + 2 * g)
+        nz, ny, nx = shp(ng[0])
+        s_old, _ = synth.make_fab((nx, ny, nz), seed=seed + bi, z=z)
+        s_old[0] = np.maximum(s_old[0], 3.0 * small_dens)
+        for c in (1, 2, 3):
+            s_old[c] = s_old[0] * 300.0 * rng.standard_normal((nz, ny, nx))
+        s_old[4] = s_old[5] + 0.5 * (s_old[1] ** 2 + s_old[2] ** 2 + s_old[3] ** 2) / s_old[0]
+        s_new = rng.standard_normal((6,) + shp(ng[1]))                       # overwritten by the call
+        ext = np.zeros((6,) + shp(ng[2]))
+        inner = tuple(slice(ng[0] - ng[2], s - (ng[0] - ng[2])) for s in (nz, ny, nx))
+        for c in range(6):
+            ext[c] = s_old[(c,) + inner] * (0.0 if c == 0 else 0.05 / dt) * rng.standard_normal(ext.shape[1:])
+        vin = tuple(slice(ng[0], s - ng[0]) for s in (nz, ny, nx))
+        hs = np.stack([s_old[(c,) + vin] * 0.1 * rng.standard_normal(shp(0)) for c in range(6)])
+        if low_density_cells:
+            flat = hs[0].reshape(-1)
+            pick = rng.choice(flat.size, low_density_cells, replace=False)
+            rho_v = s_old[(0,) + vin].reshape(-1)
+            flat[pick] = -rho_v[pick] * rng.uniform(0.9, 1.3, low_density_cells)       # new density near or below zero
+            flat[pick[0]] = small_dens - rho_v[pick[0]]                              # new density == small_dens (up to rounding): not floored or floored, both sides must agree
+        grav = rng.standard_normal((3,) + shp(ng[4])) * 1.0e3
+        rs = np.zeros((1,) + shp(ng[5]))
+        for k, v in zip(out, (s_old, s_new, ext, hs, grav, rs)):
+            out[k].append(np.ascontiguousarray(v))
+    out.update(boxes=[tuple(b) for b in boxes], ng=ng, dt=dt, a_old=a_old, a_new=a_new, small_dens=small_dens, small_temp=1.0e-2)
+    return out
+
+
 FLASH_CASES = {
     "none": {},
     "hi_now": dict(zhi_flash=5.98, T_zhi=2e4, zheii_flash=3.0, T_zheii=1.5e4),     # with z = 5.99: H flash inside the step
