@@ -17,6 +17,7 @@
  *   hc_enforce_minimum_density_batch       <- Nyx::enforce_minimum_density, floor   Source/TimeStep/Nyx_enforce_minimum_density.cpp:8-107,
  *                                             floor_density                         Source/TimeStep/Nyx_enforce_minimum_density.H:8-58
  *   hc_fab_copy|add|subtract_batch         <- MultiFab::Copy / Add / Subtract around the call  Source/Hydro/sdc_hydro.cpp:83-84,94-95,112,135
+ *   hc_init_zhi_batch                      <- Nyx::init_zhi, the cell loop            Source/Initialization/Nyx_initdata.cpp:163-213
  *   HcParams                               <- the nyx.* run-time flags of the path, Source/Driver/Nyx.cpp:116-181,
  *                                             Source/HeatCool/f_rhs_struct.H:45-101
  *   HcStats                                <- CVodeGetNum* counters (integrate_state_with_source_3d.cpp:755-790) and the
@@ -196,6 +197,10 @@ int hc_update_state_with_sources_host(int ntiles, const HcFab* s_old, const HcFa
                                       double* min_dens);
 int hc_enforce_minimum_density_host(int ntiles, const HcFab* s_old, const HcFab* s_new, const HcFab* ext_src_old, const HcFab* hydro_src,
                                     const HcFab* grav, const HcBox* tiles, double dt, double a_old, double a_new, const HcSrcParams* prm);
+/* SURVEY 8f rank 4 -- Nyx::init_zhi, the cell loop (Source/Initialization/Nyx_initdata.cpp:198-209): diag(i,j,k,Zhi_comp = 2) =
+ * zhi(i/ratio, j/ratio, k/ratio), zhi[t] = the one-component coarse reionization-redshift FAB that covers tile t coarsened by ratio
+ * (the reference fills it with VisMF::Read + ParallelCopy; nyx_b200/nyxio.py reads the VisMF file) */
+int hc_init_zhi_batch(int ntiles, const HcFab* diag, const HcFab* zhi, int ratio, const HcBox* tiles, void* stream);
 /* MultiFab::Copy / Add / Subtract (dst, src, scomp, dcomp, ncomp, nghost = tiles): dst(dcomp + n) {=, +=, -=} src(scomp + n) over the tiles */
 int hc_fab_copy_batch(int ntiles, const HcFab* dst, int dcomp, const HcFab* src, int scomp, int ncomp, const HcBox* tiles, void* stream);
 int hc_fab_add_batch(int ntiles, const HcFab* dst, int dcomp, const HcFab* src, int scomp, int ncomp, const HcBox* tiles, void* stream);

@@ -152,6 +152,51 @@ struct FabOpArgs {
     int scomp, dcomp, ncomp, op;   // op 0: copy, 1: add, 2: subtract
 };
 __global__ void __launch_bounds__(256) hc_fab_op_kernel(const __grid_constant__ FabOpArgs a) {
+    constexpr int U4 = 4;   // cells per thread and pass: all loads of a pass are issued before the first store
+    int t0 = -1;
+    for (long long base = (long long)blockIdx.x * (256 * U4); base < a.ncells; base += (long long)gridDim.x * (256 * U4)) {
+        if (t0 < 0) t0 = find_tile_by_cell(a.tiles, a.ntiles, base);
+        while (t0 + 1 < a.ntiles && a.tiles[t0 + 1].offset <= base) ++t0;
+        double* pd[U4]; const double* ps[U4];
+        long long nsd[U4], nss[U4];
+#pragma unroll
+        for (int u = 0; u < U4; ++u) {
+            const long long id = base + u * 256 + threadIdx.x;
+            pd[u] = nullptr; ps[u] = nullptr; nsd[u] = 0; nss[u] = 0;
+            if (id < a.ncells) {
+                int ti = t0;
+                while (ti + 1 < a.ntiles && a.tiles[ti + 1].offset <= id) ++ti;
+                const TileDesc& t = a.tiles[ti];
+                int i, j, k;
+                cell_of(t, id, i, j, k);
+                const HcFab& D = t.f[0]; const HcFab& S = t.f[1];
+                pd[u] = D.p + fab_off(D, i, j, k) + (long long)a.dcomp * D.nstride; nsd[u] = D.nstride;
+                ps[u] = S.p + fab_off(S, i, j, k) + (long long)a.scomp * S.nstride; nss[u] = S.nstride;
+            }
+        }
+        for (int n = 0; n < a.ncomp; ++n) {
+            double sv[U4], dv[U4];
+#pragma unroll
+            for (int u = 0; u < U4; ++u) {
+                sv[u] = 0.0; dv[u] = 0.0;
+                if (pd[u]) { sv[u] = __ldg(ps[u] + n * nss[u]); if (a.op != 0) dv[u] = pd[u][n * nsd[u]]; }
+            }
+#pragma unroll
+            for (int u = 0; u < U4; ++u)
+                if (pd[u]) pd[u][n * nsd[u]] = (a.op == 0) ? sv[u] : (a.op == 1) ? dv[u] + sv[u] : dv[u] - sv[u];
+        }
+    }
+}
+
+// Nyx::init_zhi, the cell loop (Source/Initialization/Nyx_initdata.cpp:198-209): piecewise-constant injection of the coarse reionization-redshift
+// field into diag(Zhi_comp): D_new(i,j,k,Zhi) = zhi(i/ratio, j/ratio, k/ratio) (C++ integer division).  f[0] = diag, f[1] = coarse zhi.
+struct ZhiArgs {
+    const TileDesc* tiles;
+    int ntiles;
+    long long ncells;
+    int ratio, zcomp;
+};
+__global__ void __launch_bounds__(256) hc_init_zhi_kernel(const __grid_constant__ ZhiArgs a) {
     int t0 = -1;
     for (long long id = (long long)blockIdx.x * 256 + threadIdx.x; id < a.ncells; id += (long long)gridDim.x * 256) {
         if (t0 < 0) t0 = find_tile_by_cell(a.tiles, a.ntiles, id);
@@ -159,14 +204,8 @@ __global__ void __launch_bounds__(256) hc_fab_op_kernel(const __grid_constant__ 
         const TileDesc& t = a.tiles[t0];
         int i, j, k;
         cell_of(t, id, i, j, k);
-        const HcFab& D = t.f[0]; const HcFab& S = t.f[1];
-        double* pd = D.p + fab_off(D, i, j, k) + (long long)a.dcomp * D.nstride;
-        const double* ps = S.p + fab_off(S, i, j, k) + (long long)a.scomp * S.nstride;
-        for (int n = 0; n < a.ncomp; ++n) {
-            const double s = ps[n * S.nstride];
-            double* d = pd + n * D.nstride;
-            if (a.op == 0) *d = s; else if (a.op == 1) *d = *d + s; else *d = *d - s;
-        }
+        const HcFab& D = t.f[0]; const HcFab& Z = t.f[1];
+        D.p[fab_off(D, i, j, k) + (long long)a.zcomp * D.nstride] = __ldg(Z.p + fab_off(Z, i / a.ratio, j / a.ratio, k / a.ratio));
     }
 }
 

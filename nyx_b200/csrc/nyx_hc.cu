@@ -800,13 +800,14 @@ bool valid_src_params(const HcSrcParams* p) {
 }
 
 // tile descriptors of `nf` FAB slots in stream-ordered scratch: [256 B header][tiles]; returns the number of cells
-int stage_tiles(int ntiles, const HcFab* const* fabs, int nf, const HcBox* tiles, cudaStream_t stream, char*& scratch, int& n_used, long long& ncells) {
+int stage_tiles(int ntiles, const HcFab* const* fabs, int nf, const HcBox* tiles, cudaStream_t stream, char*& scratch, int& n_used, long long& ncells,
+                int nf_check = -1) {
     std::vector<TileDesc> h_tiles; h_tiles.reserve(ntiles);
     ncells = 0; long long nchunks = 0;
     for (int t = 0; t < ntiles; ++t) {
         TileDesc td = make_tile(fabs, nf, t, tiles[t], ncells, nchunks);
         if (td.nx <= 0 || td.ny <= 0 || td.nz <= 0) continue;
-        if (!tile_inside(td, nf)) { set_err("tile %d is not contained in its FABs (or a FAB pointer is null)", t); return HC_ERR_ARG; }
+        if (!tile_inside(td, nf_check < 0 ? nf : nf_check)) { set_err("tile %d is not contained in its FABs (or a FAB pointer is null)", t); return HC_ERR_ARG; }
         ncells += (long long)td.nx * td.ny * td.nz;
         nchunks += (long long)td.cpr * td.ny * td.nz;
         h_tiles.push_back(td);
@@ -896,7 +897,7 @@ int launch_fab_op(int op, int ntiles, const HcFab* dst, int dcomp, const HcFab* 
     FabOpArgs a{};
     a.tiles = reinterpret_cast<const TileDesc*>(scratch + 256);
     a.ntiles = n_used; a.ncells = ncells; a.scomp = scomp; a.dcomp = dcomp; a.ncomp = ncomp; a.op = op;
-    const int grid = (int)std::min<long long>((ncells + 255) / 256, (long long)sms * 16);
+    const int grid = (int)std::min<long long>((ncells + 1023) / 1024, (long long)sms * 8);
     hc_fab_op_kernel<<<grid, 256, 0, stream>>>(a);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaFreeAsync(scratch, stream));
@@ -1150,6 +1151,33 @@ int hc_update_state_with_sources_host(int ntiles, const HcFab* s_old, const HcFa
     if (m < p.small_dens)   // pass 2 (rare)
         rc = hc_enforce_minimum_density_host(ntiles, s_old, s_new, ext_src_old, hydro_src, grav, tiles, dt, a_old, a_new, prm);
     return rc;
+}
+
+int hc_init_zhi_batch(int ntiles, const HcFab* diag, const HcFab* zhi, int ratio, const HcBox* tiles, void* stream_) {
+    if (ntiles < 0 || (ntiles > 0 && (!diag || !zhi || !tiles)) || ratio < 1) { set_err("bad argument"); return HC_ERR_ARG; }
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int dev; if (int rc = current_device(dev)) return rc;
+    int sms = 0; CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    for (int t = 0; t < ntiles; ++t) {
+        if (diag[t].ncomp <= ZHI) { set_err("diag FAB %d has no Zhi component (nyx.inhomo_reion = 1 allocates 3 components)", t); return HC_ERR_ARG; }
+        if (!zhi[t].p) { set_err("null zhi FAB %d", t); return HC_ERR_ARG; }
+        for (int d = 0; d < 3; ++d) {   // the coarse FAB must cover the tile coarsened by ratio
+            if (tiles[t].hi[d] < tiles[t].lo[d]) continue;
+            if (tiles[t].lo[d] / ratio < zhi[t].lo[d] || tiles[t].hi[d] / ratio > zhi[t].hi[d]) { set_err("zhi FAB %d does not cover tile/ratio", t); return HC_ERR_ARG; }
+        }
+    }
+    const HcFab* fabs[2] = {diag, zhi};
+    char* scratch; int n_used; long long ncells;
+    if (int rc = stage_tiles(ntiles, fabs, 2, tiles, stream, scratch, n_used, ncells, 1)) return rc;   // containment of the fine tile: diag only
+    if (ncells == 0) return HC_OK;
+    ZhiArgs a{};
+    a.tiles = reinterpret_cast<const TileDesc*>(scratch + 256);
+    a.ntiles = n_used; a.ncells = ncells; a.ratio = ratio; a.zcomp = ZHI;
+    const int grid = (int)std::min<long long>((ncells + 255) / 256, (long long)sms * 16);
+    hc_init_zhi_kernel<<<grid, 256, 0, stream>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaFreeAsync(scratch, stream));
+    return HC_OK;
 }
 
 int hc_fab_copy_batch(int ntiles, const HcFab* dst, int dcomp, const HcFab* src, int scomp, int ncomp, const HcBox* tiles, void* stream) {

@@ -219,3 +219,64 @@ void nyx_hc_reset_internal_energy(MultiFab& S_new, MultiFab& D_new, MultiFab& re
     check(hc_reset_internal_energy_host((int)t.size(), s.data(), d.data(), r.data(), t.data(), a, &p, small_temp, interp));
 #endif
 }
+
+
+// ---- state that rides on the path across restarts.
+// nyx.use_typical_steps = 1 caps the BDF step of the next call at dt / old_max_sundials_steps (HcParams.old_max_steps) and records the
+// largest step count (finish() above); the reference carries the two numbers through a checkpoint in the files first_max_steps /
+// second_max_steps (written Source/IO/Nyx_output.cpp:295-317 -- BOTH receive old_max_sundials_steps -- and read back by
+// Nyx::typical_values_post_restart, Source/Driver/Nyx.cpp:1625-1657, which ParallelDescriptor::Bcast's them).  Same files, same quirk;
+// the caller broadcasts.
+#include <fstream>
+int nyx_hc_write_typical_steps(const std::string& dir)
+{
+    if (!Nyx::use_typical_steps) return 0;
+    for (const char* fn : {"/first_max_steps", "/second_max_steps"}) {
+        std::ofstream File((dir + fn).c_str(), std::ios::out | std::ios::trunc);
+        if (!File.good()) return -1;
+        File.precision(15);
+        File << Nyx::old_max_sundials_steps << '\n';
+    }
+    return 0;
+}
+
+int nyx_hc_read_typical_steps(const std::string& restart_file)
+{
+    if (!Nyx::use_typical_steps) return 0;
+    {
+        std::ifstream File((restart_file + "/first_max_steps").c_str(), std::ios::in);
+        if (!File.good()) return -1;
+        File >> Nyx::old_max_sundials_steps;
+    }
+    {
+        std::ifstream File((restart_file + "/second_max_steps").c_str(), std::ios::in);
+        if (!File.good()) return -1;
+        File >> Nyx::new_max_sundials_steps;
+    }
+    return 0;
+}
+
+// Nyx::init_zhi's cell loop (Source/Initialization/Nyx_initdata.cpp:198-209); `zhi` is the coarse MultiFab the reference builds with
+// VisMF::Read + ParallelCopy just before it (:181-191, AMReX I/O and communication: unchanged), ratio = prob_res / nyx.inhomo_grid
+void nyx_hc_init_zhi(MultiFab& D_new, MultiFab& zhi, int ratio)
+{
+    if (D_new.nComp() <= 2) return;
+#ifdef AMREX_USE_GPU
+    std::vector<HcFab> d, z; std::vector<HcBox> t;
+    for (MFIter mfi(D_new); mfi.isValid(); ++mfi) {
+        d.push_back(to_fab(D_new.array(mfi))); z.push_back(to_fab(zhi.array(mfi))); t.push_back(to_box(mfi.validbox()));
+    }
+    if (t.empty()) return;
+    check(hc_init_zhi_batch((int)t.size(), d.data(), z.data(), ratio, t.data(), nullptr));
+    check(hc_sync(nullptr));
+#else
+    // host FABs: an initialisation-time copy of one component; staging it through the device would only add two transfers
+    for (MFIter mfi(D_new); mfi.isValid(); ++mfi) {
+        const Box& bx = mfi.validbox();
+        const auto fab_zhi = zhi.array(mfi);
+        const auto fab_D_new = D_new.array(mfi);
+        for (int k = bx.smallEnd(2); k <= bx.bigEnd(2); ++k) for (int j = bx.smallEnd(1); j <= bx.bigEnd(1); ++j) for (int i = bx.smallEnd(0); i <= bx.bigEnd(0); ++i)
+            fab_D_new(i, j, k, 2) = fab_zhi(i / ratio, j / ratio, k / ratio);
+    }
+#endif
+}

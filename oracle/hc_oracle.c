@@ -1243,3 +1243,10 @@ int hco_sources_finish_box(const hco_params* p, const hco_fab* uin, const hco_fa
     }
     return 0;
 }
+
+/* the cell loop of Nyx::init_zhi (Source/Initialization/Nyx_initdata.cpp:198-209) over one box */
+int hco_init_zhi_box(const hco_fab* diag, const hco_fab* zhi, const int lo[3], const int hi[3], int ratio) {
+    for (int k = lo[2]; k <= hi[2]; ++k) for (int j = lo[1]; j <= hi[1]; ++j) for (int i = lo[0]; i <= hi[0]; ++i)
+        *at(diag, i, j, k, ZHI) = *at(zhi, i / ratio, j / ratio, k / ratio, 0);
+    return 0;
+}

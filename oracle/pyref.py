@@ -297,6 +297,12 @@ class Port:
                                        small_dens, small_temp, int(decide < small_dens), sdc)
         return m
 
+    def init_zhi(self, diag, diag_lo, zhi, zhi_lo, lo, hi, ratio):
+        l3 = C.c_int * 3
+        fp = C.POINTER(HcoFab)
+        self.lib.hco_init_zhi_box.argtypes = [fp, fp, l3, l3, C.c_int]
+        self.lib.hco_init_zhi_box(C.byref(fab_of(diag, diag_lo)), C.byref(fab_of(zhi, zhi_lo)), l3(*lo), l3(*hi), ratio)
+
     def eos_box(self, state, diag, lo, hi, a, params=None):
         p = params or self.params()
         sf, df = fab_of(state, lo), fab_of(diag, lo)
