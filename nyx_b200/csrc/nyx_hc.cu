@@ -560,6 +560,14 @@ int current_device(int& dev) {
     return HC_OK;
 }
 
+// multiprocessor count, queried once per device (the rank-2/4 streaming launchers do not need the rate tables of DeviceTables)
+int sm_count_of(int dev, int& sms) {
+    static int cached[64] = {0};
+    if (!cached[dev]) CUDA_TRY(cudaDeviceGetAttribute(&cached[dev], cudaDevAttrMultiProcessorCount, dev));
+    sms = cached[dev];
+    return HC_OK;
+}
+
 bool valid_params(const HcParams* p) {
     return p && p->rtol > 0.0 && p->atol_factor >= 0.0 && p->h_species > 0.0 && p->h_species <= 1.0;
 }
@@ -851,7 +859,7 @@ SrcArgs make_src_args(double dt, double a_old, double a_new, const HcSrcParams& 
 int launch_sources(int mode, int ntiles, const HcFab* const* fabs, const HcBox* tiles, double dt, double a_old, double a_new, const HcSrcParams& p,
                    double* min_dens_out, unsigned long long* ext_min, cudaStream_t stream) {
     int dev; if (int rc = current_device(dev)) return rc;
-    int sms = 0; CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    int sms = 0; if (int rc = sm_count_of(dev, sms)) return rc;
     char* scratch; int n_used; long long ncells;
     if (int rc = stage_tiles(ntiles, fabs, 5, tiles, stream, scratch, n_used, ncells)) return rc;
     if (min_dens_out) *min_dens_out = DBL_MAX;
@@ -887,7 +895,7 @@ int check_src_fabs(int ntiles, const HcFab* s_old, const HcFab* s_new, const HcF
 
 int launch_fab_op(int op, int ntiles, const HcFab* dst, int dcomp, const HcFab* src, int scomp, int ncomp, const HcBox* tiles, cudaStream_t stream) {
     int dev; if (int rc = current_device(dev)) return rc;
-    int sms = 0; CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    int sms = 0; if (int rc = sm_count_of(dev, sms)) return rc;
     for (int t = 0; t < ntiles; ++t)
         if (dcomp < 0 || scomp < 0 || ncomp < 0 || dcomp + ncomp > dst[t].ncomp || scomp + ncomp > src[t].ncomp) { set_err("component range outside FAB %d", t); return HC_ERR_ARG; }
     const HcFab* fabs[2] = {dst, src};
@@ -1157,7 +1165,7 @@ int hc_init_zhi_batch(int ntiles, const HcFab* diag, const HcFab* zhi, int ratio
     if (ntiles < 0 || (ntiles > 0 && (!diag || !zhi || !tiles)) || ratio < 1) { set_err("bad argument"); return HC_ERR_ARG; }
     cudaStream_t stream = (cudaStream_t)stream_;
     int dev; if (int rc = current_device(dev)) return rc;
-    int sms = 0; CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    int sms = 0; if (int rc = sm_count_of(dev, sms)) return rc;
     for (int t = 0; t < ntiles; ++t) {
         if (diag[t].ncomp <= ZHI) { set_err("diag FAB %d has no Zhi component (nyx.inhomo_reion = 1 allocates 3 components)", t); return HC_ERR_ARG; }
         if (!zhi[t].p) { set_err("null zhi FAB %d", t); return HC_ERR_ARG; }
@@ -1196,7 +1204,7 @@ int hc_fab_subtract_batch(int ntiles, const HcFab* dst, int dcomp, const HcFab* 
 int hc_measure_fp64_peak(double* flops_per_s) {
     if (!flops_per_s) { set_err("null argument"); return HC_ERR_ARG; }
     int dev; if (int rc = current_device(dev)) return rc;
-    int sms = 0; CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    int sms = 0; if (int rc = sm_count_of(dev, sms)) return rc;
     const int blocks = sms * 8, threads = 256, iters = 4096;
     double* out = nullptr;
     CUDA_TRY(cudaMalloc((void**)&out, (size_t)blocks * threads * sizeof(double)));
