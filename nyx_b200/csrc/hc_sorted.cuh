@@ -22,8 +22,19 @@ namespace sorted {
 // ---- scalar fields of a lane kept in shared memory between phases (the Nordsieck arrays occupy slots 0..ARR_DOUBLES-1)
 #define HC_SD_COMMON(X) X(req_t) X(req_y) X(rho) X(e0) X(lastT) X(lastNe) X(ewt) X(acor) X(ftemp) X(tn) X(h) X(hprime) X(eta) X(hscale) \
     X(etamax) X(rl1) X(gamma) X(gammap) X(crate) X(delp) X(saved_tq5) X(M) X(gammasv) X(saved_t) X(delta) X(yy_ft) X(hg) X(hub) X(hlb) X(e_final)
+// (outT, outNe, IR -- the SDC finalize results that wait for the final EOS solve when reionization heating is on -- have no slots of their
+//  own: a lane in PC_FINAL_EOS keeps them in the slots of the cvHin locals hg, hub, hlb, which are dead after the initial step.  592 instead
+//  of 616 bytes per lane: 384 instead of 352 lanes fit.)
+#if !defined(HC_STRUCT_ALIAS_OUT)
+#define HC_STRUCT_ALIAS_OUT 1
+#endif
+#if HC_STRUCT_ALIAS_OUT
+#define HC_SD_STRUCT(X) X(jh) X(rho_src) X(rhoe_src) X(e_src) X(rho_out) X(rhoe_new) X(reset_src) X(zhi) X(lastNh) X(lastRho) X(eos_nhe0) \
+    X(eos_nhepp)
+#else
 #define HC_SD_STRUCT(X) X(jh) X(rho_src) X(rhoe_src) X(e_src) X(rho_out) X(rhoe_new) X(reset_src) X(zhi) X(lastNh) X(lastRho) X(eos_nhe0) \
     X(eos_nhepp) X(outT) X(outNe) X(IR)
+#endif
 #define HC_COUNT(name) +1
 constexpr int ND_COMMON = 0 HC_SD_COMMON(HC_COUNT);
 constexpr int ND_STRUCT = 0 HC_SD_STRUCT(HC_COUNT);
@@ -222,6 +233,9 @@ __global__ void __launch_bounds__(LANES, HC_SORTED_CTAS) hc_sorted_kernel(const 
                 HC_SD_COMMON(HC_LD)
                 if (PATH == PATH_STRUCT) { HC_SD_STRUCT(HC_LD) }
 #undef HC_LD
+#if HC_STRUCT_ALIAS_OUT
+                if (PATH == PATH_STRUCT) { ln.outT = ln.hg; ln.outNe = ln.hub; ln.IR = ln.hlb; }   // meaningful in PC_FINAL_EOS only
+#endif
                 int w = SI_CNT0;
 #define HC_LDI(name) ln.name = si[(w++) * LANES + my];
                 HC_SI_WORDS(HC_LDI)
@@ -293,6 +307,9 @@ __global__ void __launch_bounds__(LANES, HC_SORTED_CTAS) hc_sorted_kernel(const 
             pack_ints(ln, w0, w1);
             si[SI_W0 * LANES + my] = (int)w0; si[SI_W1 * LANES + my] = (int)w1;
             {
+#if HC_STRUCT_ALIAS_OUT
+                if (PATH == PATH_STRUCT && ln.pc == PC_FINAL_EOS) { ln.hg = ln.outT; ln.hub = ln.outNe; ln.hlb = ln.IR; }
+#endif
                 int s = SD0;
 #define HC_ST(name) sd[(s++) * LANES + my] = ln.name;
                 HC_SD_COMMON(HC_ST)

@@ -18,7 +18,7 @@ from nyx_b200 import capi, sharded, synth  # noqa: E402
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 box = int(sys.argv[2]) if len(sys.argv) > 2 else 128
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
-hc = capi.NyxHC()
+hc = capi.NyxHC(os.environ["HC_LIB"]) if os.environ.get("HC_LIB") else capi.NyxHC()   # HC_LIB: build-variant experiments
 hc.tables_upload(hc.tabulate_rates(os.path.join(ROOT, "tests", "golden", "TREECOOL_middle"), synth.mean_rhob()))
 peak = hc.measure_fp64_peak()
 boxes = sharded.box_list(n, box)
