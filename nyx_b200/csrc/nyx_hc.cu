@@ -19,6 +19,7 @@
 #include <cstdint>
 #include <cfloat>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <mutex>
@@ -566,6 +567,11 @@ int current_device(int& dev) {
 // on the streaming kernels of SURVEY 8f rank 2: 1.45 ms per call for a 1.15 ms kernel).  A slot is reused only after the copy that read it
 // last has completed (one event per slot).  Also raises the release threshold of the device's stream-ordered pool once, so that the scratch
 // of a call is not handed back to the driver at every synchronisation.
+__global__ void hc_copy_words_kernel(unsigned long long* __restrict__ dst, const unsigned long long* __restrict__ src, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[i];
+}
+static_assert(sizeof(TileDesc) % 8 == 0, "tile descriptors are copied in 8-byte words");
 struct StageRing {
     static constexpr int SLOTS = 8;
     static constexpr size_t SLOT_BYTES = 256 * 1024;
@@ -587,7 +593,8 @@ int copy_small_h2d(int dev, void* dst, const void* src, size_t bytes, cudaStream
         CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
         r.pool_set = true;
     }
-    if (bytes > StageRing::SLOT_BYTES) {   // thousands of tiles: the pageable path (a one-off drain is small against such a launch)
+    static const bool pageable = std::getenv("NYX_HC_PAGEABLE_DESC") != nullptr;   // diagnostics: the old behaviour, for A/B timing
+    if (pageable || bytes > StageRing::SLOT_BYTES) {   // thousands of tiles: the pageable path (a one-off drain is small against such a launch)
         CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream));
         return HC_OK;
     }
@@ -601,7 +608,12 @@ int copy_small_h2d(int dev, void* dst, const void* src, size_t bytes, cudaStream
     CUDA_TRY(cudaEventSynchronize(r.ev[slot]));   // a never-recorded event is complete
     char* pin = r.base + (size_t)slot * StageRing::SLOT_BYTES;
     std::memcpy(pin, src, bytes);
-    CUDA_TRY(cudaMemcpyAsync(dst, pin, bytes, cudaMemcpyHostToDevice, stream));
+    // a KERNEL reads the pinned slot (zero-copy) and writes the device copy: stream-ordered on the compute engine.  A DMA copy of these few
+    // kilobytes shares a copy engine with the bulk FAB transfers of the host-buffer pipeline and waited behind them (measured: 518-530 ms
+    // instead of 507 ms per 512^3 step end to end).
+    const int words = (int)((bytes + 7) / 8);
+    hc_copy_words_kernel<<<(words + 255) / 256, 256, 0, stream>>>(reinterpret_cast<unsigned long long*>(dst), reinterpret_cast<const unsigned long long*>(pin), words);
+    CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(r.ev[slot], stream));
     return HC_OK;
 }
@@ -751,6 +763,16 @@ struct HostSlot {
 struct HostPipe {
     cudaStream_t h2d = nullptr, comp = nullptr, d2h = nullptr;
     bool ready = false;
+    // Three persistent device slabs, used round-robin by the groups of a call: one copying in, one computing, one copying out.  A slab is
+    // handed to group g once the D2H of group g-3 has finished (event, waited for by the h2d STREAM: the host never blocks).  No allocator in
+    // the loop: with stream-ordered allocation the blocks a group released on the d2h stream came back to the h2d stream with a dependency
+    // on that release, and the H2D of group g+1 stopped overlapping kernel g as soon as the host no longer paced the loop by accident.
+    static constexpr int NSLAB = 3;
+    char* slab[NSLAB] = {nullptr, nullptr, nullptr};
+    size_t cap[NSLAB] = {0, 0, 0};
+    cudaEvent_t slab_free[NSLAB] = {};
+    bool slab_busy[NSLAB] = {false, false, false};
+    std::mutex call_mu;   // host-buffer calls on one device run one after the other (they share the slabs and the three streams)
 };
 HostPipe g_pipe[64];
 constexpr int HOST_GROUPS = 8;
@@ -767,6 +789,7 @@ int host_pipe(int dev, HostPipe*& hp) {
         CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, dev));
         unsigned long long keep = ~0ull;
         CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        for (int i = 0; i < HostPipe::NSLAB; ++i) CUDA_TRY(cudaEventCreateWithFlags(&hp->slab_free[i], cudaEventDisableTiming));
         hp->ready = true;
     }
     return HC_OK;
@@ -797,18 +820,34 @@ int run_host(int path, int ntiles, std::vector<HostSlot>& slots, const HcBox* ti
     auto new_event = [&](cudaEvent_t& e) { cudaError_t r = cudaEventCreateWithFlags(&e, cudaEventDisableTiming); if (r == cudaSuccess) events.push_back(e); return r; };
     int rc = HC_OK;
     std::vector<std::vector<HcFab>> dfab(nf);
-    for (int t0 = 0; t0 < ntiles && rc == HC_OK;) {
+    std::lock_guard<std::mutex> call_lock(hp->call_mu);
+    int group = 0;
+    for (int t0 = 0; t0 < ntiles && rc == HC_OK; ++group) {
         int t1 = t0; long long acc = 0;
         while (t1 < ntiles && (t1 == t0 || acc + cells[t1] <= per_group)) acc += cells[t1++];
         const int n = t1 - t0;
-        std::vector<double*> bufs;
+        // this group's slab: large enough for all its FABs (256-byte aligned), free once its previous user has copied out
+        const int b = group % HostPipe::NSLAB;
+        size_t need = 0;
+        for (int s = 0; s < nf; ++s)
+            for (int i = 0; i < n; ++i) need += (fab_doubles(slots[s].host[t0 + i]) * sizeof(double) + 255) / 256 * 256;
+        if (need > hp->cap[b]) {
+            if (hp->slab_busy[b]) CUDA_TRY(cudaEventSynchronize(hp->slab_free[b]));
+            if (hp->slab[b]) CUDA_TRY(cudaFree(hp->slab[b]));
+            hp->slab[b] = nullptr; hp->cap[b] = 0;
+            CUDA_TRY(cudaMalloc((void**)&hp->slab[b], need));
+            hp->cap[b] = need;
+            hp->slab_busy[b] = false;
+        }
+        if (hp->slab_busy[b]) CUDA_TRY(cudaStreamWaitEvent(hp->h2d, hp->slab_free[b], 0));
+        size_t off = 0;
         for (int s = 0; s < nf; ++s) {
             dfab[s].assign(slots[s].host + t0, slots[s].host + t1);
             for (int i = 0; i < n; ++i) {
                 const HcFab& h = slots[s].host[t0 + i];
-                double* d = nullptr;
-                CUDA_TRY(cudaMallocAsync((void**)&d, fab_doubles(h) * sizeof(double), hp->h2d));
-                bufs.push_back(d); dfab[s][i].p = d;
+                double* d = reinterpret_cast<double*>(hp->slab[b] + off);
+                off += (fab_doubles(h) * sizeof(double) + 255) / 256 * 256;
+                dfab[s][i].p = d;
                 for (int c : slots[s].in) {
                     if (c >= h.ncomp) continue;
                     CUDA_TRY(cudaMemcpyAsync(d + (size_t)c * h.nstride, h.p + (size_t)c * h.nstride, (size_t)h.nstride * sizeof(double),
@@ -836,7 +875,8 @@ int run_host(int path, int ntiles, std::vector<HostSlot>& slots, const HcBox* ti
                                              cudaMemcpyDeviceToHost, hp->d2h));
                 }
             }
-        for (double* d : bufs) CUDA_TRY(cudaFreeAsync(d, hp->d2h));
+        CUDA_TRY(cudaEventRecord(hp->slab_free[b], hp->d2h));
+        hp->slab_busy[b] = true;
         t0 = t1;
     }
     if (rc == HC_OK && stats) CUDA_TRY(cudaMemcpyAsync(stats, dstats, sizeof(HcStats), cudaMemcpyDeviceToHost, hp->comp));
