@@ -77,3 +77,30 @@ def algorithmic_flops(stats):
     234 per RHS evaluation (174 + 3 x 20), 60 per step attempt, 99 per finalize EOS solve."""
     d = stats if isinstance(stats, dict) else stats.as_dict()
     return 186.0 * d["sum_ne_iters"] + 234.0 * (d["sum_nfe"] + d["sum_nfe_ls"]) + 60.0 * d["sum_attempts"] + 99.0 * d["sum_eos"]
+
+
+def allreduce_min(value, device=None):
+    """min over ranks of one double: the global S_new.min(Density_comp) of Nyx::enforce_minimum_density
+    (Source/TimeStep/Nyx_enforce_minimum_density.cpp:22) -- the one real exchange step of the rank-2 row"""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return float(value)
+    t = torch.tensor([float(value)], dtype=torch.float64)
+    if device is not None:
+        t = t.to(device)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return float(t.item())
+
+
+def update_state_with_sources_sharded(update_local, enforce_local, small_dens, device=None):
+    """Nyx::update_state_with_sources over the boxes of this rank, with the reference's GLOBAL density-floor decision.
+    update_local() runs hc_update_state_with_sources_batch on the local boxes and returns their minimum new density (it has already
+    applied the floor if that minimum is below small_dens); enforce_local() runs hc_enforce_minimum_density_batch on them.
+    Returns (local_min, global_min, enforced_here_afterwards)."""
+    local_min = update_local()
+    global_min = allreduce_min(local_min, device)
+    late = (global_min < small_dens) and not (local_min < small_dens)
+    if late:
+        enforce_local()
+    return local_min, global_min, late

@@ -261,6 +261,12 @@ st["max_nst"] = 7 + 5 * rank
 g = sharded.allreduce_stats(st)
 assert g["n_cells"] == 64 ** 3 and g["sum_nst"] == 300 and g["max_nst"] == 12, g
 assert sorted(mine + sharded.local_boxes(boxes, 2, 1 - rank)) == list(range(8))
+# SURVEY 8f rank 2: the global density-floor decision of enforce_minimum_density (MIN all-reduce), three cases
+for case, mins, want_late in (("nobody below", (2.0, 3.0), (False, False)), ("rank 1 below", (2.0, 0.5), (True, False)), ("both below", (0.2, 0.5), (False, False))):
+    calls = []
+    lm, gm, late = sharded.update_state_with_sources_sharded(lambda: (calls.append("update"), mins[rank])[1], lambda: calls.append("enforce"), small_dens=1.0)
+    assert lm == mins[rank] and gm == min(mins) and late == want_late[rank], (case, rank, lm, gm, late)
+    assert calls == (["update", "enforce"] if want_late[rank] else ["update"]), (case, calls)
 dist.destroy_process_group()
 print("ok", rank)
 """
