@@ -406,7 +406,8 @@ def main():
                            "rtol": 1e-4, "atol_factor": 1e-4, "l2": "inputs (%.1f GB per GPU) are larger than L2" % (8e-9 * sum(comps.values()) * ncell_local),
                            "restore": "mutated components are reset from a pristine device copy between steps, outside the event pairs",
                            "parallelism": "boxes sharded over %d GPU(s), no data-path collective, one scalar all-reduce of diagnostics" % world},
-                "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps, "roofline": roofline, "cpu_baseline": cpu,
+                "clocks": clocks, "e2e": e2e, "gpu_launches": 2 * args.steps,   # per step: hc_copy_words_kernel (tile descriptors) + hc_sorted_kernel
+                "roofline": roofline, "cpu_baseline": cpu,
                 "stats": gstats, "ms_steps": ms_steps, "wall_s_timed_loop": wall, "gen_s": t_gen}
         print(json.dumps(line), file=_RESULT_OUT, flush=True)
     if world > 1:
