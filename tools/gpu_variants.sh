@@ -1,5 +1,6 @@
 #!/bin/bash
 # times every library variant under build/variants/ (and the default build) on a 256^3 vec step and a 128^3 struct step: best of 6 / 4 repetitions
+# (tools/gpu_ab_e2e.sh: A/B of the descriptor staging path on the end-to-end leg of bench.py)
 mkdir -p gpurun_out
 for f in nyx_b200/csrc/libnyx_hc.so build/variants/*.so; do
   echo "== $f"
