@@ -575,7 +575,8 @@ static_assert(sizeof(TileDesc) % 8 == 0, "tile descriptors are copied in 8-byte 
 struct StageRing {
     static constexpr int SLOTS = 8;
     static constexpr size_t SLOT_BYTES = 256 * 1024;
-    char* base = nullptr;
+    char* base = nullptr;       // host address of the pinned, device-mapped ring
+    char* dev_base = nullptr;   // the same memory as the device sees it (equal to `base` under unified addressing)
     cudaEvent_t ev[SLOTS] = {};
     int next = 0;
     bool ready = false, pool_set = false;
@@ -599,7 +600,8 @@ int copy_small_h2d(int dev, void* dst, const void* src, size_t bytes, cudaStream
         return HC_OK;
     }
     if (!r.ready) {
-        CUDA_TRY(cudaMallocHost((void**)&r.base, StageRing::SLOTS * StageRing::SLOT_BYTES));
+        CUDA_TRY(cudaHostAlloc((void**)&r.base, StageRing::SLOTS * StageRing::SLOT_BYTES, cudaHostAllocMapped));
+        CUDA_TRY(cudaHostGetDevicePointer((void**)&r.dev_base, r.base, 0));
         for (int i = 0; i < StageRing::SLOTS; ++i) CUDA_TRY(cudaEventCreateWithFlags(&r.ev[i], cudaEventDisableTiming));
         r.ready = true;
     }
@@ -612,7 +614,8 @@ int copy_small_h2d(int dev, void* dst, const void* src, size_t bytes, cudaStream
     // kilobytes shares a copy engine with the bulk FAB transfers of the host-buffer pipeline and waited behind them (measured: 518-530 ms
     // instead of 507 ms per 512^3 step end to end).
     const int words = (int)((bytes + 7) / 8);
-    hc_copy_words_kernel<<<(words + 255) / 256, 256, 0, stream>>>(reinterpret_cast<unsigned long long*>(dst), reinterpret_cast<const unsigned long long*>(pin), words);
+    hc_copy_words_kernel<<<(words + 255) / 256, 256, 0, stream>>>(reinterpret_cast<unsigned long long*>(dst),
+                                                                  reinterpret_cast<const unsigned long long*>(r.dev_base + (size_t)slot * StageRing::SLOT_BYTES), words);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(r.ev[slot], stream));
     return HC_OK;
