@@ -69,3 +69,21 @@ def test_struct_golden(port, gold, name, z, n, seed, src, flash):
     # the error cell by cell.  The two modes OF THE REFERENCE therefore differ by more than 10 x rtol in a few stiff cells
     # (up to 41 % in one cell of struct_z2_src).  Bulk within 10 x rtol, outliers rare:
     assert np.median(rel) < 3e-4 and np.mean(rel > 1e-3) < 0.04
+
+
+@pytest.mark.parametrize("case", ["nofloor", "floor"])
+def test_update_state_with_sources_golden(port, case):
+    """the port against outputs of the reference's own Nyx_update_state_with_sources.cpp (tests/golden/make_sources_golden.py),
+    bit for bit, with and without cells below small_dens"""
+    import copy
+    from tests.golden import make_sources_golden as msg
+    gold = np.load(os.path.join(os.path.dirname(GOLD), "sources_golden.npz"))
+    name, z, seed, low = [c for c in msg.CASES if c[0] == case][0]
+    d = msg.inputs(z, seed, low)
+    p = copy.deepcopy(d)
+    m = port.update_state_with_sources(d["boxes"], p["s_old"], p["s_new"], p["ext_src"], p["hydro_src"], p["grav"], d["dt"], d["a_old"], d["a_new"],
+                                       d["small_dens"], d["small_temp"], ng=d["ng"][:5])
+    assert (m < d["small_dens"]) == (low > 0)
+    for bi in range(len(msg.BOXES)):
+        assert np.array_equal(p["s_new"][bi], gold[f"{case}.s_new.{bi}"])
+        assert np.array_equal(p["hydro_src"][bi], gold[f"{case}.hydro_src.{bi}"])
