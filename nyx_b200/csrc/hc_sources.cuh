@@ -148,42 +148,36 @@ __global__ void __launch_bounds__(SRC_THREADS) hc_sources_kernel(const __grid_co
 struct FabOpArgs {
     const TileDesc* tiles;
     int ntiles;
-    long long ncells;
+    long long ncells, nchunks;
     int scomp, dcomp, ncomp, op;   // op 0: copy, 1: add, 2: subtract
 };
+// One warp per chunk (a piece of an x-row, at most CHUNK_MAX = 256 cells): the tile lookup and the (j, k) decode cost three integer divisions
+// per CHUNK instead of two per CELL -- with three memory operations per cell the per-cell index arithmetic was what bounded this kernel
+// (0.255 ms = 48 % of HBM peak for 3.4e7 cells whatever the grid).  Lanes stride over the row: loads of up to 8 cells per lane first, then stores.
 __global__ void __launch_bounds__(256) hc_fab_op_kernel(const __grid_constant__ FabOpArgs a) {
-    constexpr int U4 = 4;   // cells per thread and pass: all loads of a pass are issued before the first store
-    int t0 = -1;
-    for (long long base = (long long)blockIdx.x * (256 * U4); base < a.ncells; base += (long long)gridDim.x * (256 * U4)) {
-        if (t0 < 0) t0 = find_tile_by_cell(a.tiles, a.ntiles, base);
-        while (t0 + 1 < a.ntiles && a.tiles[t0 + 1].offset <= base) ++t0;
-        double* pd[U4]; const double* ps[U4];
-        long long nsd[U4], nss[U4];
+    const unsigned lane = threadIdx.x & 31u;
+    const long long nwarps = (long long)gridDim.x * 8;
+    for (long long ch = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); ch < a.nchunks; ch += nwarps) {
+        const TileDesc& t = a.tiles[find_tile_by_chunk(a.tiles, a.ntiles, ch)];
+        const unsigned local = (unsigned)(ch - t.chunk_begin);
+        const unsigned row = local / (unsigned)t.cpr, piece = local - row * (unsigned)t.cpr;
+        const unsigned kk = row / (unsigned)t.ny;
+        const int k = t.lo[2] + (int)kk, j = t.lo[1] + (int)(row - kk * (unsigned)t.ny);
+        const int x0 = t.lo[0] + (int)piece * t.chunk_len;
+        const int len = min(t.chunk_len, t.lo[0] + t.nx - x0);
+        const HcFab& D = t.f[0]; const HcFab& S = t.f[1];
+        double* pd = D.p + fab_off(D, x0, j, k) + (long long)a.dcomp * D.nstride + lane;
+        const double* ps = S.p + fab_off(S, x0, j, k) + (long long)a.scomp * S.nstride + lane;
+        for (int n = 0; n < a.ncomp; ++n, pd += D.nstride, ps += S.nstride) {
+            double sv[8], dv[8];
 #pragma unroll
-        for (int u = 0; u < U4; ++u) {
-            const long long id = base + u * 256 + threadIdx.x;
-            pd[u] = nullptr; ps[u] = nullptr; nsd[u] = 0; nss[u] = 0;
-            if (id < a.ncells) {
-                int ti = t0;
-                while (ti + 1 < a.ntiles && a.tiles[ti + 1].offset <= id) ++ti;
-                const TileDesc& t = a.tiles[ti];
-                int i, j, k;
-                cell_of(t, id, i, j, k);
-                const HcFab& D = t.f[0]; const HcFab& S = t.f[1];
-                pd[u] = D.p + fab_off(D, i, j, k) + (long long)a.dcomp * D.nstride; nsd[u] = D.nstride;
-                ps[u] = S.p + fab_off(S, i, j, k) + (long long)a.scomp * S.nstride; nss[u] = S.nstride;
-            }
-        }
-        for (int n = 0; n < a.ncomp; ++n) {
-            double sv[U4], dv[U4];
-#pragma unroll
-            for (int u = 0; u < U4; ++u) {
+            for (int u = 0; u < 8; ++u) {
                 sv[u] = 0.0; dv[u] = 0.0;
-                if (pd[u]) { sv[u] = __ldg(ps[u] + n * nss[u]); if (a.op != 0) dv[u] = pd[u][n * nsd[u]]; }
+                if ((int)lane + 32 * u < len) { sv[u] = __ldg(ps + 32 * u); if (a.op != 0) dv[u] = pd[32 * u]; }
             }
 #pragma unroll
-            for (int u = 0; u < U4; ++u)
-                if (pd[u]) pd[u][n * nsd[u]] = (a.op == 0) ? sv[u] : (a.op == 1) ? dv[u] + sv[u] : dv[u] - sv[u];
+            for (int u = 0; u < 8; ++u)
+                if ((int)lane + 32 * u < len) pd[32 * u] = (a.op == 0) ? sv[u] : (a.op == 1) ? dv[u] + sv[u] : dv[u] - sv[u];
         }
     }
 }
