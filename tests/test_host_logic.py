@@ -217,6 +217,26 @@ def test_cabi_fails_loudly_without_device(built):
         hc.integrate_vec_host([capi.fab_of_numpy(state, (0, 0, 0))], [capi.fab_of_numpy(diag, (0, 0, 0))],
                               [capi.make_box((0, 0, 0), (3, 3, 3))], 0.25, 1e-3)
     assert np.array_equal(state, synth.make_fab((4, 4, 4), seed=1, z=3.0)[0])     # and nothing was computed behind our back
+    # the rows either side of the path likewise: host and device entry points
+    d = util.sources_inputs(seed=3)
+    before = [x.copy() for x in d["s_new"]]
+    fabs = {k: [capi.fab_of_numpy(x, tuple(c - g for c in bx[:3])) for x, bx in zip(d[k], d["boxes"])]
+            for k, g in zip(("s_old", "s_new", "ext_src", "hydro_src", "grav"), d["ng"])}
+    tiles = [capi.make_box(bx[:3], bx[3:]) for bx in d["boxes"]]
+    prm = hc.src_params(small_dens=d["small_dens"], small_temp=d["small_temp"])
+    for host in (True, False):
+        with pytest.raises(capi.HcError):
+            hc.update_state_with_sources_batch(fabs["s_old"], fabs["s_new"], fabs["ext_src"], fabs["hydro_src"], fabs["grav"], tiles, d["dt"],
+                                               d["a_old"], d["a_new"], prm, host=host)
+        with pytest.raises(capi.HcError):
+            hc.enforce_minimum_density_batch(fabs["s_old"], fabs["s_new"], fabs["ext_src"], fabs["hydro_src"], fabs["grav"], tiles, d["dt"],
+                                             d["a_old"], d["a_new"], prm, host=host)
+    with pytest.raises(capi.HcError):
+        hc.fab_op_batch("add", fabs["ext_src"], 4, fabs["hydro_src"], 0, 1, tiles)
+    with pytest.raises(capi.HcError):
+        hc.compute_new_temp_batch([capi.fab_of_numpy(state, (0, 0, 0))], [capi.fab_of_numpy(diag, (0, 0, 0))], [capi.make_box((0, 0, 0), (3, 3, 3))],
+                                  0.25, 1e-2, 1e9, 0)
+    assert all(np.array_equal(x, y) for x, y in zip(before, d["s_new"]))
     with pytest.raises(capi.HcError, match="missing"):
         capi.NyxHC(path="/nonexistent/libnyx_hc.so")
 
