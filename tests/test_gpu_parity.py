@@ -639,3 +639,74 @@ def test_fab_copy_add_subtract(hc_lib):
         assert np.array_equal(x.cpu().numpy(), w)
     with pytest.raises(capi.HcError, match="component range"):
         hc_lib.fab_op_batch("copy", fe, 6, fi, 0, 1, tiles)
+
+
+def test_sources_full_size_properties(hc_lib):
+    """Rank-2 row at a full-size level (256^3 cells, beyond what the oracle follows in seconds), through size-independent properties:
+    (a) identity: no sources, no gravity, a_new == a_old  ->  S_new == S_old bit for bit and the reported minimum is min(rho);
+    (b) decomposition independence: the same field as one box and as 64 boxes (each its own FAB) gives bit-identical S_new and minimum;
+    (c) the floor acts exactly on the cells below small_dens, which end at (small_dens, 0 momentum + gravity, floor energy), and hydro_src(rho)
+        is S_new(rho) - S_old(rho) everywhere; (d) determinism."""
+    torch = _torch()
+    n = 256
+    gen = torch.Generator(device="cuda").manual_seed(77)
+    z = 3.0
+    a_old, dt = 1.0 / (1.0 + z), synth.step_dt(z)
+    a_new = synth.a_after(z, dt)
+    rho_b = synth.mean_rhob()
+    s_old = torch.randn((6, n, n, n), generator=gen, device="cuda", dtype=torch.float64)
+    s_old[0] = rho_b * torch.exp(s_old[0].clamp(-3, 3))      # >= 0.05 rho_b: five times small_dens
+    s_old[4:6] = s_old[4:6].abs() * 1e12 * s_old[0]
+    zeros6 = torch.zeros_like(s_old)
+    grav0 = torch.zeros((3, n, n, n), dtype=torch.float64, device="cuda")
+    lo, hi = (0, 0, 0), (n - 1,) * 3
+    prm = hc_lib.src_params(small_dens=1.0e-2 * rho_b, small_temp=1.0e-2)
+
+    def run(s_in, ext, hs, grav, a1, nsplit=1):
+        m = n // nsplit
+        keep, fabs, tiles = [], [[] for _ in range(5)], []
+        for kb in range(nsplit):
+            for jb in range(nsplit):
+                for ib in range(nsplit):
+                    sl = (slice(None), slice(kb * m, (kb + 1) * m), slice(jb * m, (jb + 1) * m), slice(ib * m, (ib + 1) * m))
+                    blo = (ib * m, jb * m, kb * m)
+                    parts = [x[sl].contiguous() if nsplit > 1 else x for x in (s_in, None, ext, hs, grav) if x is not None]
+                    parts.insert(1, torch.full_like(parts[0], float("nan")))
+                    keep.append((sl, parts))
+                    for slot, p in enumerate(parts):
+                        fabs[slot].append(capi.fab_of_torch(p, blo))
+                    tiles.append(capi.make_box(blo, tuple(c + m - 1 for c in blo)))
+        mn = hc_lib.update_state_with_sources_batch(fabs[0], fabs[1], fabs[2], fabs[3], fabs[4], tiles, dt, a_old, a1, prm)
+        out = torch.empty_like(s_in)
+        hs_out = torch.empty_like(s_in)
+        for sl, parts in keep:
+            out[sl] = parts[1]
+            hs_out[sl] = parts[3]
+        return out, hs_out, mn
+
+    out, _, mn = run(s_old, zeros6, zeros6.clone(), grav0, a_old)                               # (a)
+    # a_old * u / a_old and a_old^2 * u / a_old^2 are exact only up to one rounding each way: the reference's expressions, not an identity in floating point
+    assert torch.equal(out[0], s_old[0]) and mn == float(s_old[0].min())
+    assert torch.allclose(out[1:], s_old[1:], rtol=4e-16, atol=0.0)
+    ext = 0.05 / dt * s_old * torch.randn(s_old.shape, generator=gen, device="cuda", dtype=torch.float64)
+    ext[0] = 0.0
+    hs = 0.1 * s_old * torch.randn(s_old.shape, generator=gen, device="cuda", dtype=torch.float64).clamp(-3, 3)
+    grav = 1.0e3 * torch.randn((3, n, n, n), generator=gen, device="cuda", dtype=torch.float64)
+    o1, h1, m1 = run(s_old, ext, hs.clone(), grav, a_new)                                       # no cell below small_dens
+    assert m1 > prm.small_dens and torch.equal(h1, hs)
+    o1b, _, m1b = run(s_old, ext, hs.clone(), grav, a_new)
+    assert torch.equal(o1, o1b) and m1 == m1b                                                   # (d)
+    o4, h4, m4 = run(s_old, ext, hs.clone(), grav, a_new, nsplit=4)                             # (b)
+    assert torch.equal(o1, o4) and torch.equal(h1, h4) and m1 == m4
+    hs_low = hs.clone()
+    hs_low[0, ::37, ::41, ::43] = -1.5 * s_old[0, ::37, ::41, ::43]                             # (c): these cells go below small_dens
+    o2, h2, m2 = run(s_old, ext, hs_low.clone(), grav, a_new)
+    o2s, h2s, m2s = run(s_old, ext, hs_low.clone(), grav, a_new, nsplit=4)
+    assert m2 < prm.small_dens and m2 == m2s and torch.equal(o2, o2s) and torch.equal(h2, h2s)
+    low = torch.zeros((n, n, n), dtype=torch.bool, device="cuda")
+    low[::37, ::41, ::43] = True
+    assert torch.equal(o2[0] == prm.small_dens, low)
+    assert torch.equal(h2[0], o2[0] - s_old[0]) and torch.equal(h2[1:], hs_low[1:])
+    assert torch.equal(o2[:, ~low], o1[:, ~low])                                                # untouched cells: same values as without the floor
+    mom = s_old[0, low] * grav[0, low] * (dt / a_new)                                           # floored momentum 0 + gravity
+    assert torch.equal(o2[1, low], mom) and bool((o2[5, low] == o2[5, low][0]).all())
