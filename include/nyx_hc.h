@@ -201,6 +201,7 @@ int hc_enforce_minimum_density_host(int ntiles, const HcFab* s_old, const HcFab*
  * zhi(i/ratio, j/ratio, k/ratio), zhi[t] = the one-component coarse reionization-redshift FAB that covers tile t coarsened by ratio
  * (the reference fills it with VisMF::Read + ParallelCopy; nyx_b200/nyxio.py reads the VisMF file) */
 int hc_init_zhi_batch(int ntiles, const HcFab* diag, const HcFab* zhi, int ratio, const HcBox* tiles, void* stream);
+int hc_init_zhi_host(int ntiles, const HcFab* diag, const HcFab* zhi, int ratio, const HcBox* tiles);
 /* MultiFab::Copy / Add / Subtract (dst, src, scomp, dcomp, ncomp, nghost = tiles): dst(dcomp + n) {=, +=, -=} src(scomp + n) over the tiles */
 int hc_fab_copy_batch(int ntiles, const HcFab* dst, int dcomp, const HcFab* src, int scomp, int ncomp, const HcBox* tiles, void* stream);
 int hc_fab_add_batch(int ntiles, const HcFab* dst, int dcomp, const HcFab* src, int scomp, int ncomp, const HcBox* tiles, void* stream);

@@ -118,6 +118,7 @@ def declare(lib, prefix="hc_"):
     for name in ("hc_fab_copy_batch", "hc_fab_add_batch", "hc_fab_subtract_batch"):
         getattr(lib, name).argtypes = [C.c_int, fp, C.c_int, fp, C.c_int, C.c_int, bp, C.c_void_p]
     lib.hc_init_zhi_batch.argtypes = [C.c_int, fp, fp, C.c_int, bp, C.c_void_p]
+    lib.hc_init_zhi_host.argtypes = [C.c_int, fp, fp, C.c_int, bp]
     lib.hc_measure_fp64_peak.argtypes = [_dp]
     lib.hc_selftest_log10.argtypes = [_dp, _dp, C.POINTER(C.c_int), C.c_longlong]
     lib.hc_sync.argtypes = [C.c_void_p]
@@ -259,6 +260,10 @@ class NyxHC:
     def init_zhi_batch(self, diag, zhi, ratio, tiles, stream=None):
         """Nyx::init_zhi cell loop: diag(i,j,k,2) = zhi(i/ratio, j/ratio, k/ratio)"""
         self.check(self.lib.hc_init_zhi_batch(len(tiles), self._arr(diag, HcFab), self._arr(zhi, HcFab), ratio, self._arr(tiles, HcBox), stream))
+
+    def init_zhi_host(self, diag, zhi, ratio, tiles):
+        """the same with HOST FABs (CPU build of the host application): staged through the device"""
+        self.check(self.lib.hc_init_zhi_host(len(tiles), self._arr(diag, HcFab), self._arr(zhi, HcFab), ratio, self._arr(tiles, HcBox)))
 
     def selftest_log10(self, x):
         """log10 of a float64 array through the kernels' table-driven fast path -> (y, bad)"""

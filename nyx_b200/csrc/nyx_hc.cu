@@ -813,6 +813,50 @@ int host_pipe(int dev, HostPipe*& hp) {
 }
 
 using GroupLauncher = std::function<int(int n, const HcFab* const* fabs, const HcBox* tiles, cudaStream_t stream)>;
+
+// D2H of component c of one FAB restricted to the cells of `b` (the tile): used for components that were NOT uploaded (pure outputs), so
+// that host cells outside the tile -- ghost cells, other tiles of the same FAB -- keep their values.  Contiguous when the tile spans the
+// FAB in x and y (one block of nz planes), a pitched 3-D copy otherwise.
+int copy_tile_d2h(const HcFab& h, const double* dbase, int c, const HcBox& b, cudaStream_t stream) {
+    const long long nx = b.hi[0] - b.lo[0] + 1, ny = b.hi[1] - b.lo[1] + 1, nz = b.hi[2] - b.lo[2] + 1;
+    if (nx <= 0 || ny <= 0 || nz <= 0) return HC_OK;
+    const long long off = (b.lo[0] - h.lo[0]) + (b.lo[1] - h.lo[1]) * h.jstride + (b.lo[2] - h.lo[2]) * h.kstride + (long long)c * h.nstride;
+    if (nx == h.jstride && ny * h.jstride == h.kstride) {
+        CUDA_TRY(cudaMemcpyAsync(h.p + off, dbase + off, (size_t)(nz * h.kstride) * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        return HC_OK;
+    }
+    if (h.kstride % h.jstride != 0) { set_err("FAB strides are not those of a box (kstride is not a multiple of jstride)"); return HC_ERR_ARG; }
+    cudaMemcpy3DParms prm{};
+    const size_t pitch = (size_t)h.jstride * sizeof(double), rows = (size_t)(h.kstride / h.jstride);
+    // the pitched pointers start at the tile's first cell: the row pitch and the rows per plane are the FAB's
+    prm.srcPtr = make_cudaPitchedPtr(const_cast<double*>(dbase) + off, pitch, (size_t)nx * sizeof(double), rows);
+    prm.dstPtr = make_cudaPitchedPtr(h.p + off, pitch, (size_t)nx * sizeof(double), rows);
+    prm.extent = make_cudaExtent((size_t)nx * sizeof(double), (size_t)ny, (size_t)nz);
+    prm.kind = cudaMemcpyDeviceToHost;
+    CUDA_TRY(cudaMemcpy3DAsync(&prm, stream));
+    return HC_OK;
+}
+
+// everything a host-buffer call must hand back on EVERY exit path (early error returns included)
+struct HostCallGuard {
+    HostPipe* hp;
+    unsigned long long* dstats = nullptr;
+    std::vector<cudaEvent_t> events;
+    explicit HostCallGuard(HostPipe* p) : hp(p) {}
+    ~HostCallGuard() {
+        // drain the three streams first: the slabs and the events may still be in use by queued work
+        cudaStreamSynchronize(hp->h2d); cudaStreamSynchronize(hp->comp); cudaStreamSynchronize(hp->d2h);
+        for (int i = 0; i < HostPipe::NSLAB; ++i) hp->slab_busy[i] = false;
+        if (dstats) cudaFreeAsync(dstats, hp->comp);
+        for (cudaEvent_t e : events) cudaEventDestroy(e);
+    }
+    cudaError_t new_event(cudaEvent_t& e) {
+        cudaError_t r = cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+        if (r == cudaSuccess) events.push_back(e);
+        return r;
+    }
+};
+
 int run_host(int path, int ntiles, std::vector<HostSlot>& slots, const HcBox* tiles, const Consts& k, HcStats* stats, const EosOpts* eos = nullptr,
              const GroupLauncher* custom = nullptr) {
     int dev; if (int rc = current_device(dev)) return rc;
@@ -821,6 +865,26 @@ int run_host(int path, int ntiles, std::vector<HostSlot>& slots, const HcBox* ti
     const int nf = (int)slots.size();
     for (const HostSlot& sl : slots)
         for (int t = 0; t < ntiles; ++t) if (!sl.host[t].p) { set_err("null host FAB"); return HC_ERR_ARG; }
+    // Several tiles may share a FAB (a tiled MFIter of a CPU build of AMReX): such tiles get ONE device copy, uploaded once, and stay in
+    // one group.  They must be consecutive (as MFIter delivers them); anything else is rejected rather than silently losing updates.
+    auto shares_fab = [&](int t, int u) {
+        for (int s = 0; s < nf; ++s) if (slots[s].host[t].p == slots[s].host[u].p) return true;
+        return false;
+    };
+    {
+        std::vector<const double*> seen;
+        for (int s = 0; s < nf; ++s) {
+            seen.clear();
+            for (int t = 0; t < ntiles; ++t) {
+                const double* p = slots[s].host[t].p;
+                if (t > 0 && p == slots[s].host[t - 1].p) continue;
+                if (std::find(seen.begin(), seen.end(), p) != seen.end()) {
+                    set_err("tiles %d...: tiles that share a host FAB must be consecutive in the tile list", t); return HC_ERR_ARG;
+                }
+                seen.push_back(p);
+            }
+        }
+    }
     // groups of consecutive tiles with about 1/HOST_GROUPS of the cells each
     long long total = 0;
     std::vector<long long> cells(ntiles);
@@ -830,27 +894,28 @@ int run_host(int path, int ntiles, std::vector<HostSlot>& slots, const HcBox* ti
         total += cells[t];
     }
     const long long per_group = std::max<long long>((total + HOST_GROUPS - 1) / HOST_GROUPS, 1);
-    unsigned long long* dstats = nullptr;
-    CUDA_TRY(cudaMallocAsync((void**)&dstats, 128, hp->comp));
+    std::lock_guard<std::mutex> call_lock(hp->call_mu);
+    HostCallGuard guard(hp);
+    CUDA_TRY(cudaMallocAsync((void**)&guard.dstats, 128, hp->comp));
+    unsigned long long* dstats = guard.dstats;
     CUDA_TRY(cudaMemsetAsync(dstats, 0, 128, hp->comp));
-    std::vector<cudaEvent_t> events;
-    auto new_event = [&](cudaEvent_t& e) { cudaError_t r = cudaEventCreateWithFlags(&e, cudaEventDisableTiming); if (r == cudaSuccess) events.push_back(e); return r; };
     int rc = HC_OK;
     std::vector<std::vector<HcFab>> dfab(nf);
-    std::lock_guard<std::mutex> call_lock(hp->call_mu);
     int group = 0;
     for (int t0 = 0; t0 < ntiles && rc == HC_OK; ++group) {
         // the first group is half a share: its H2D is not hidden behind any kernel; the last group then is the remaining half share, whose
         // D2H is not hidden either (measured: 496.8 ms instead of 507.0 ms per 512^3 step; a finer ramp 1/32, 1/16, 1/8 ... 3/32, 1/16: 495.5 ms, not kept)
         const long long share = (group == 0 && HOST_TAPER) ? std::max<long long>(per_group / 2, 1) : per_group;
         int t1 = t0; long long acc = 0;
-        while (t1 < ntiles && (t1 == t0 || acc + cells[t1] <= share)) acc += cells[t1++];
+        while (t1 < ntiles && (t1 == t0 || acc + cells[t1] <= share || shares_fab(t1, t1 - 1))) acc += cells[t1++];
         const int n = t1 - t0;
+        // first tile of each FAB of this group (per slot): the one that owns the device copy
+        auto first_of = [&](int s, int i) { int j = i; while (j > 0 && slots[s].host[t0 + j - 1].p == slots[s].host[t0 + i].p) --j; return j; };
         // this group's slab: large enough for all its FABs (256-byte aligned), free once its previous user has copied out
         const int b = group % HostPipe::NSLAB;
         size_t need = 0;
         for (int s = 0; s < nf; ++s)
-            for (int i = 0; i < n; ++i) need += (fab_doubles(slots[s].host[t0 + i]) * sizeof(double) + 255) / 256 * 256;
+            for (int i = 0; i < n; ++i) if (first_of(s, i) == i) need += (fab_doubles(slots[s].host[t0 + i]) * sizeof(double) + 255) / 256 * 256;
         if (need > hp->cap[b]) {
             if (hp->slab_busy[b]) CUDA_TRY(cudaEventSynchronize(hp->slab_free[b]));
             if (hp->slab[b]) CUDA_TRY(cudaFree(hp->slab[b]));
@@ -865,6 +930,8 @@ int run_host(int path, int ntiles, std::vector<HostSlot>& slots, const HcBox* ti
             dfab[s].assign(slots[s].host + t0, slots[s].host + t1);
             for (int i = 0; i < n; ++i) {
                 const HcFab& h = slots[s].host[t0 + i];
+                const int own = first_of(s, i);
+                if (own != i) { dfab[s][i].p = dfab[s][own].p; continue; }   // another tile of the same FAB: share its device copy
                 double* d = reinterpret_cast<double*>(hp->slab[b] + off);
                 off += (fab_doubles(h) * sizeof(double) + 255) / 256 * 256;
                 dfab[s][i].p = d;
@@ -876,7 +943,7 @@ int run_host(int path, int ntiles, std::vector<HostSlot>& slots, const HcBox* ti
             }
         }
         cudaEvent_t e_in, e_k;
-        CUDA_TRY(new_event(e_in)); CUDA_TRY(new_event(e_k));
+        CUDA_TRY(guard.new_event(e_in)); CUDA_TRY(guard.new_event(e_k));
         CUDA_TRY(cudaEventRecord(e_in, hp->h2d));
         CUDA_TRY(cudaStreamWaitEvent(hp->comp, e_in, 0));
         std::vector<const HcFab*> fabs(nf);
@@ -889,10 +956,15 @@ int run_host(int path, int ntiles, std::vector<HostSlot>& slots, const HcBox* ti
         for (int s = 0; s < nf; ++s)
             for (int i = 0; i < n; ++i) {
                 const HcFab& h = slots[s].host[t0 + i];
+                const bool owner = (first_of(s, i) == i);
                 for (int c : slots[s].out) {
                     if (c >= h.ncomp) continue;
-                    CUDA_TRY(cudaMemcpyAsync(h.p + (size_t)c * h.nstride, dfab[s][i].p + (size_t)c * h.nstride, (size_t)h.nstride * sizeof(double),
-                                             cudaMemcpyDeviceToHost, hp->d2h));
+                    const bool uploaded = std::find(slots[s].in.begin(), slots[s].in.end(), c) != slots[s].in.end();
+                    if (uploaded) {
+                        // the device copy holds the whole component: one contiguous copy per FAB
+                        if (owner) CUDA_TRY(cudaMemcpyAsync(h.p + (size_t)c * h.nstride, dfab[s][i].p + (size_t)c * h.nstride, (size_t)h.nstride * sizeof(double),
+                                                            cudaMemcpyDeviceToHost, hp->d2h));
+                    } else if (int rc2 = copy_tile_d2h(h, dfab[s][i].p, c, tiles[t0 + i], hp->d2h)) return rc2;   // pure output: the tile's cells only
                 }
             }
         CUDA_TRY(cudaEventRecord(hp->slab_free[b], hp->d2h));
@@ -900,11 +972,7 @@ int run_host(int path, int ntiles, std::vector<HostSlot>& slots, const HcBox* ti
         t0 = t1;
     }
     if (rc == HC_OK && stats) CUDA_TRY(cudaMemcpyAsync(stats, dstats, sizeof(HcStats), cudaMemcpyDeviceToHost, hp->comp));
-    CUDA_TRY(cudaFreeAsync(dstats, hp->comp));
-    CUDA_TRY(cudaStreamSynchronize(hp->comp));
-    CUDA_TRY(cudaStreamSynchronize(hp->d2h));
-    for (cudaEvent_t e : events) cudaEventDestroy(e);
-    return rc;
+    return rc;   // the guard drains the streams and releases the scratch
 }
 
 
@@ -1141,7 +1209,8 @@ int hc_integrate_vec_host(int ntiles, const HcFab* state, const HcFab* diag, con
     if (g_rates.empty()) { set_err("hc_tables_upload has not been called"); return HC_ERR_NO_TABLES; }
     if (stats) std::memset(stats, 0, sizeof *stats);
     const Consts k = make_consts_vec(g_rates.data(), *prm, a, dt);
-    std::vector<HostSlot> slots = {{state, {DENS, EDEN, EINT}, {EDEN, EINT}}, {diag, {TEMP, NE}, {TEMP, NE}}};
+    // diag(Temp, Ne) are dead inputs of the Strang path (eos_hc.H:151; load_cell never reads them): pure outputs, not uploaded
+    std::vector<HostSlot> slots = {{state, {DENS, EDEN, EINT}, {EDEN, EINT}}, {diag, {}, {TEMP, NE}}};
     return run_host(PATH_VEC, ntiles, slots, tiles, k, stats);
 }
 
@@ -1293,6 +1362,17 @@ int hc_init_zhi_batch(int ntiles, const HcFab* diag, const HcFab* zhi, int ratio
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaFreeAsync(scratch, stream));
     return HC_OK;
+}
+
+int hc_init_zhi_host(int ntiles, const HcFab* diag, const HcFab* zhi, int ratio, const HcBox* tiles) {
+    if (ntiles < 0 || (ntiles > 0 && (!diag || !zhi || !tiles)) || ratio < 1) { set_err("bad argument"); return HC_ERR_ARG; }
+    if (ntiles == 0) return HC_OK;
+    // diag(Zhi) is a pure output (only the tile's cells travel back), the coarse zhi FAB a pure input
+    std::vector<HostSlot> slots = {{diag, {}, {ZHI}}, {zhi, {0}, {}}};
+    GroupLauncher fill = [&](int n, const HcFab* const* fabs, const HcBox* tl, cudaStream_t st) {
+        return hc_init_zhi_batch(n, fabs[0], fabs[1], ratio, tl, st);
+    };
+    return run_host(-1, ntiles, slots, tiles, Consts{}, nullptr, nullptr, &fill);
 }
 
 int hc_fab_copy_batch(int ntiles, const HcFab* dst, int dcomp, const HcFab* src, int scomp, int ncomp, const HcBox* tiles, void* stream) {

@@ -123,12 +123,14 @@ int Nyx::integrate_state_vec(MultiFab& S_old, MultiFab& D_old, const Real& a, co
 // HC/integrate_state_vec_3d.cpp:367-396: valid cells AND the ghost cells of S_old (growntilebox of an untiled MFIter)
 int Nyx::integrate_state_grownvec(MultiFab& S_old, MultiFab& D_old, const Real& a, const Real& delta_time)
 {
-    const long int store_steps = new_max_sundials_steps;
+    // the FIRST Strang half-step works on the OTHER counter (integrate_state_vec_3d.cpp:376,392): the step cap is dt / old_max and the
+    // largest step count goes back into old_max_sundials_steps (the one the checkpoint files carry, Nyx_output.cpp:295-317)
+    const long int store_steps = old_max_sundials_steps;
     std::vector<HcFab> s, d; std::vector<HcBox> t;
     for (MFIter mfi(S_old); mfi.isValid(); ++mfi) {
         s.push_back(to_fab(S_old.array(mfi))); d.push_back(to_fab(D_old.array(mfi))); t.push_back(to_box(mfi.growntilebox()));
     }
-    return vec_batch(s, d, t, a, delta_time, store_steps, new_max_sundials_steps);
+    return vec_batch(s, d, t, a, delta_time, store_steps, old_max_sundials_steps);
 }
 
 // HC/integrate_state_vec_3d.cpp:72-365: one tile
@@ -261,22 +263,16 @@ int nyx_hc_read_typical_steps(const std::string& restart_file)
 void nyx_hc_init_zhi(MultiFab& D_new, MultiFab& zhi, int ratio)
 {
     if (D_new.nComp() <= 2) return;
-#ifdef AMREX_USE_GPU
     std::vector<HcFab> d, z; std::vector<HcBox> t;
     for (MFIter mfi(D_new); mfi.isValid(); ++mfi) {
         d.push_back(to_fab(D_new.array(mfi))); z.push_back(to_fab(zhi.array(mfi))); t.push_back(to_box(mfi.validbox()));
     }
     if (t.empty()) return;
+#ifdef AMREX_USE_GPU
     check(hc_init_zhi_batch((int)t.size(), d.data(), z.data(), ratio, t.data(), nullptr));
     check(hc_sync(nullptr));
 #else
-    // host FABs: an initialisation-time copy of one component; staging it through the device would only add two transfers
-    for (MFIter mfi(D_new); mfi.isValid(); ++mfi) {
-        const Box& bx = mfi.validbox();
-        const auto fab_zhi = zhi.array(mfi);
-        const auto fab_D_new = D_new.array(mfi);
-        for (int k = bx.smallEnd(2); k <= bx.bigEnd(2); ++k) for (int j = bx.smallEnd(1); j <= bx.bigEnd(1); ++j) for (int i = bx.smallEnd(0); i <= bx.bigEnd(0); ++i)
-            fab_D_new(i, j, k, 2) = fab_zhi(i / ratio, j / ratio, k / ratio);
-    }
+    // CPU build of AMReX: the same kernel through the host-buffer staging path (no CPU loop on the product path)
+    check(hc_init_zhi_host((int)t.size(), d.data(), z.data(), ratio, t.data()));
 #endif
 }

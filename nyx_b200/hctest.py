@@ -58,8 +58,28 @@ def write_chunk(path, fabs, los):
             write_fab(f, fabs[k], los[k])
 
 
+def _read_bytes(path):
+    """the file, or its xz-compressed copy `path`.xz (how committed fixtures are stored)"""
+    if not os.path.exists(path) and os.path.exists(path + ".xz"):
+        import lzma
+        with lzma.open(path + ".xz", "rb") as f:
+            return f.read()
+    return open(path, "rb").read()
+
+
+def read_fabs(path, names):
+    """a file of len(names) FABs back to back -> (fabs, los) keyed by `names`"""
+    buf = _read_bytes(path)
+    pos, fabs, los = 0, {}, {}
+    for k in names:
+        fabs[k], los[k], pos = read_fab(buf, pos)
+    if pos != len(buf):
+        raise ValueError(f"{path}: {len(buf) - pos} trailing bytes after the {len(names)} FABs")
+    return fabs, los
+
+
 def read_chunk(path):
-    buf = open(path, "rb").read()
+    buf = _read_bytes(path)
     pos, fabs, los = 0, {}, {}
     for k in FAB_ORDER:
         fabs[k], los[k], pos = read_fab(buf, pos)
