@@ -16,11 +16,23 @@
 //   * nyx.use_sundials_fused / sundials_alloc_type / sundials_atomic_reductions are accepted and ignored;
 //   * FAB memory must be device-accessible when AMReX is built with AMREX_USE_GPU; in a CPU build of AMReX the host-buffer
 //     entry points stage the touched components through pinned memory.
+//
+// This file compiles against the reference's REAL headers (Source/Driver/Nyx.H + AMReX 23.04): tests/test_dropin_real.py builds it with
+// the flags of the reference's own GNUmake build, links it with the UNMODIFIED strang_reactions.cpp, sdc_reactions.cpp, Nyx_advance.cpp, ...
+// objects in place of the two replaced translation units, and runs the resulting Nyx executable on the GPU.  The protected Nyx statics
+// (sundials_reltol, use_typical_steps, ...) are therefore only read inside Nyx:: member functions.
 #include <AMReX_MultiFab.H>
 #include <AMReX_ParmParse.H>
 #include <Nyx.H>
+#if __has_include(<atomic_rates_data.H>)
+#include <atomic_rates_data.H>   // the reference's AtomicRates image, filled by its own tabulate_rates (Nyx::heatcool_setup, unchanged)
+#define NYX_HC_HAVE_ATOMIC_RATES 1
+#endif
 
 #include <algorithm>
+#include <cstring>
+#include <fstream>
+#include <string>
 #include <vector>
 
 #include "nyx_hc.h"
@@ -47,19 +59,26 @@ HcBox to_box(const Box& b) {
     return r;
 }
 
-// the nyx.* run-time flags of the path: Nyx statics (Source/Driver/Nyx.cpp:116-181) + what ode_eos_setup re-parses on every
-// tile call in the reference (Source/HeatCool/f_rhs_struct.H:45-101); parsed once per call here
-HcParams params_from_nyx(long int old_max_steps) {
+// the nyx.* run-time flags of the path: Nyx statics (Source/Driver/Nyx.cpp:116-181; the protected ones are handed in by the member
+// functions) + what ode_eos_setup re-parses on every tile call in the reference (Source/HeatCool/f_rhs_struct.H:45-101); parsed once per call
+struct NyxFlags {
+    Real reltol, abstol;
+    int use_typical_steps, use_constraint;
+};
+// inside a Nyx:: member function
+#define NYX_HC_FLAGS() NyxFlags{sundials_reltol, sundials_abstol, use_typical_steps, use_sundials_constraint}
+
+HcParams make_params(const NyxFlags& fl, long int old_max_steps) {
     HcParams p;
     hc_default_params(&p);
-    p.rtol = Nyx::sundials_reltol;
-    p.atol_factor = Nyx::sundials_abstol;
+    p.rtol = fl.reltol;
+    p.atol_factor = fl.abstol;
     p.h_species = Nyx::h_species;
     p.gamma_minus_1 = Nyx::gamma - 1.0;
     p.max_steps = 2000;                               // CVodeSetMaxNumSteps(cvode_mem, 2000)
-    p.use_typical_steps = Nyx::use_typical_steps;
+    p.use_typical_steps = fl.use_typical_steps;
     p.old_max_steps = old_max_steps;                  // CVodeSetMaxStep(cvode_mem, delta_time / old_max_steps)
-    p.use_constraint = Nyx::use_sundials_constraint;
+    p.use_constraint = fl.use_constraint;
     ParmParse pp_nyx("nyx");
     pp_nyx.query("inhomo_reion", p.inhomo_reion);
     pp_nyx.query("uvb_density_A", p.uvb_density_A);
@@ -70,27 +89,51 @@ HcParams params_from_nyx(long int old_max_steps) {
     pp_nyx.query("reionization_T_zHeII", p.T_zheii);
     return p;
 }
+// for the rows next to the path (EOS only: no integrator flags needed)
+HcParams eos_params() { return make_params(NyxFlags{1e-4, 1e-4, 0, 0}, 3); }
 
 int check(int rc) {
     if (rc != HC_OK) amrex::Abort(std::string("nyx_hc: ") + hc_last_error());
     return 0;   // like the reference: per-cell integrator failures are not errors (they are counted in HcStats)
 }
 
-void finish(const HcStats& st, long int& new_max_steps) {
-    g_last_stats = st;
-    if (Nyx::use_typical_steps) new_max_steps = std::max<long int>(st.max_nst, new_max_steps);   // integrate_state_vec_3d.cpp:285-290
+// The rate tables.  A host application that calls nyx_hc_setup() from Nyx::heatcool_setup has uploaded them already; otherwise (callers
+// and set-up code COMPLETELY unchanged) the image the reference's own tabulate_rates left in atomic_rates_glob is uploaded on first use.
+bool g_tables_ready = false;
+void ensure_tables() {
+    if (g_tables_ready) return;
+#if defined(NYX_HC_HAVE_ATOMIC_RATES)
+    static_assert(sizeof(AtomicRates) == sizeof(double) * HC_RATES_DOUBLES, "AtomicRates image layout (Source/EOS/atomic_rates_data.H:22-49)");
+    if (atomic_rates_glob == nullptr) amrex::Abort("nyx_hc: atomic_rates_glob is not allocated (heat_cool_type != 11?)");
+    std::vector<double> img(HC_RATES_DOUBLES);
+#ifdef AMREX_USE_GPU
+    amrex::Gpu::dtoh_memcpy(img.data(), atomic_rates_glob, sizeof(AtomicRates));
+#else
+    std::memcpy(img.data(), atomic_rates_glob, sizeof(AtomicRates));
+#endif
+    check(hc_tables_upload(img.data(), img.size()));
+    g_tables_ready = true;
+#else
+    amrex::Abort("nyx_hc: call nyx_hc_setup(treecool_file, mean_rhob) from Nyx::heatcool_setup first");
+#endif
 }
 
-int vec_batch(std::vector<HcFab>& s, std::vector<HcFab>& d, std::vector<HcBox>& t, Real a, Real dt, long int old_max, long int& new_max) {
+void finish(const HcStats& st, int use_typical, long int& new_max_steps) {
+    g_last_stats = st;
+    if (use_typical) new_max_steps = std::max<long int>(st.max_nst, new_max_steps);   // integrate_state_vec_3d.cpp:285-290
+}
+
+int vec_batch(std::vector<HcFab>& s, std::vector<HcFab>& d, std::vector<HcBox>& t, Real a, Real dt, const NyxFlags& fl, long int old_max, long int& new_max) {
     if (t.empty()) return 0;
-    const HcParams p = params_from_nyx(old_max);
+    ensure_tables();
+    const HcParams p = make_params(fl, old_max);
     HcStats st{};
 #ifdef AMREX_USE_GPU
     const int rc = hc_integrate_vec_batch((int)t.size(), s.data(), d.data(), t.data(), a, dt, &p, &st, nullptr, nullptr);
 #else
     const int rc = hc_integrate_vec_host((int)t.size(), s.data(), d.data(), t.data(), a, dt, &p, &st);
 #endif
-    finish(st, new_max);
+    finish(st, fl.use_typical_steps, new_max);
     return check(rc);
 }
 
@@ -106,6 +149,7 @@ extern "C" int nyx_hc_setup(const char* treecool_path, double mean_rhob)
     int rc = hc_tabulate_rates(treecool_path, mean_rhob, rates.data());
     if (rc == HC_OK) rc = hc_tables_upload(rates.data(), rates.size());
     if (rc != HC_OK) amrex::Abort(std::string("nyx_hc_setup: ") + hc_last_error());
+    g_tables_ready = true;
     return rc;
 }
 
@@ -117,7 +161,7 @@ int Nyx::integrate_state_vec(MultiFab& S_old, MultiFab& D_old, const Real& a, co
     for (MFIter mfi(S_old); mfi.isValid(); ++mfi) {
         s.push_back(to_fab(S_old.array(mfi))); d.push_back(to_fab(D_old.array(mfi))); t.push_back(to_box(mfi.validbox()));
     }
-    return vec_batch(s, d, t, a, delta_time, store_steps, new_max_sundials_steps);
+    return vec_batch(s, d, t, a, delta_time, NYX_HC_FLAGS(), store_steps, new_max_sundials_steps);
 }
 
 // HC/integrate_state_vec_3d.cpp:367-396: valid cells AND the ghost cells of S_old (growntilebox of an untiled MFIter)
@@ -130,7 +174,7 @@ int Nyx::integrate_state_grownvec(MultiFab& S_old, MultiFab& D_old, const Real& 
     for (MFIter mfi(S_old); mfi.isValid(); ++mfi) {
         s.push_back(to_fab(S_old.array(mfi))); d.push_back(to_fab(D_old.array(mfi))); t.push_back(to_box(mfi.growntilebox()));
     }
-    return vec_batch(s, d, t, a, delta_time, store_steps, old_max_sundials_steps);
+    return vec_batch(s, d, t, a, delta_time, NYX_HC_FLAGS(), store_steps, old_max_sundials_steps);
 }
 
 // HC/integrate_state_vec_3d.cpp:72-365: one tile
@@ -138,13 +182,15 @@ int Nyx::integrate_state_vec_mfin(Array4<Real> const& state4, Array4<Real> const
                                   const Real& delta_time, long int& old_max_steps, long int& new_max_steps)
 {
     std::vector<HcFab> s{to_fab(state4)}, d{to_fab(diag_eos4)}; std::vector<HcBox> t{to_box(tbx)};
-    return vec_batch(s, d, t, a, delta_time, old_max_steps, new_max_steps);
+    return vec_batch(s, d, t, a, delta_time, NYX_HC_FLAGS(), old_max_steps, new_max_steps);
 }
 
 namespace {
-int struct_batch(std::vector<HcFab> f[6], std::vector<HcBox>& t, Real a, Real a_end, Real dt, int sdc_iter, long int old_max, long int& new_max) {
+int struct_batch(std::vector<HcFab> f[6], std::vector<HcBox>& t, Real a, Real a_end, Real dt, int sdc_iter, const NyxFlags& fl, long int old_max,
+                 long int& new_max) {
     if (t.empty()) return 0;
-    const HcParams p = params_from_nyx(old_max);
+    ensure_tables();
+    const HcParams p = make_params(fl, old_max);
     HcStats st{};
 #ifdef AMREX_USE_GPU
     const int rc = hc_integrate_struct_batch((int)t.size(), f[0].data(), f[1].data(), f[2].data(), f[3].data(), f[4].data(), f[5].data(),
@@ -153,16 +199,104 @@ int struct_batch(std::vector<HcFab> f[6], std::vector<HcBox>& t, Real a, Real a_
     const int rc = hc_integrate_struct_host((int)t.size(), f[0].data(), f[1].data(), f[2].data(), f[3].data(), f[4].data(), f[5].data(),
                                             t.data(), a, a_end, dt, sdc_iter, &p, &st);
 #endif
-    finish(st, new_max);
+    finish(st, fl.use_typical_steps, new_max);
     return check(rc);
 }
 }  // namespace
 
-// HC/integrate_state_with_source_3d.cpp:50-185 (the hctest dump/replay hooks :82-125 stay with the reference's I/O layer)
+#if !defined(NYX_HC_SHIM_BUILD)
+// ---- the hctest isolation-test hooks of the SDC path (HC/integrate_state_with_source_3d.cpp:82-125; file layout of sdc_writeOn / sdc_readFrom,
+// HC/f_rhs_struct.H:587-697): nyx.hctest_example_write = 1 dumps the six MultiFabs of a call (+ the ParmParse table and the replay keys,
+// + BoxArray / DistributionMapping) before it runs, nyx.hctest_example_read = 1 loads them instead of the caller's data -- what
+// Exec/HeatCoolTests replays.  Host-side I/O through AMReX's own writers, so the files are interchangeable with the reference's.
+namespace {
+void hctest_write(MultiFab& S_old, MultiFab& S_new, MultiFab& D_old, MultiFab& hydro_src, MultiFab& IR, MultiFab& reset_src, int n_tiles,
+                  Real a, Real a_end, Real delta_time, int index, const std::string& f_inputs, const std::string& f_badmap, const std::string& f_chunk)
+{
+    {
+        std::ofstream ofs_inputs(f_inputs.c_str());
+        ParmParse::dumpTable(ofs_inputs, true);
+        ofs_inputs << "nyx.initial_z = " << 1 / a - 1 << std::endl;
+        ofs_inputs << "nyx.final_z = " << 1 / a_end - 1 << std::endl;
+        ofs_inputs << "nyx.fixed_dt = " << delta_time << std::endl;
+        ofs_inputs << "nyx.hctest_filename_inputs = " << f_inputs << std::endl;
+        ofs_inputs << "nyx.hctest_filename_badmap = " << f_badmap << std::endl;
+        ofs_inputs << "nyx.hctest_filename_chunk = " << f_chunk << std::endl;
+        ofs_inputs << "nyx.hctest_endIndex = " << n_tiles << std::endl;
+        ofs_inputs << "nyx.hctest_example_write = 0" << std::endl;
+        ofs_inputs << "nyx.hctest_example_read = 1" << std::endl;
+        ofs_inputs << "nyx.do_dm_particles = 0" << std::endl;
+        ofs_inputs << "nyx.do_hydro = 0" << std::endl;
+        ofs_inputs << "nyx.hctest_example_index = " << index << std::endl;
+    }
+    {
+        std::ofstream ofs(f_badmap.c_str());
+        S_old.boxArray().writeOn(ofs);
+        S_old.DistributionMap().writeOn(ofs);
+    }
+    // one chunk per local FAB, the six FABs in the reference's order
+    for (MFIter mfi(S_old); mfi.isValid(); ++mfi) {
+        std::ofstream ofs((f_chunk + std::to_string(mfi.index())).c_str());
+        S_old[mfi].writeOn(ofs); D_old[mfi].writeOn(ofs); S_new[mfi].writeOn(ofs);
+        hydro_src[mfi].writeOn(ofs); reset_src[mfi].writeOn(ofs); IR[mfi].writeOn(ofs);
+    }
+}
+
+void hctest_read(MultiFab& S_old, MultiFab& S_new, MultiFab& D_old, MultiFab& hydro_src, MultiFab& IR, MultiFab& reset_src,
+                 const std::string& f_badmap, const std::string& f_chunk)
+{
+    BoxArray grids;
+    DistributionMapping dmap;
+    std::ifstream ifs(f_badmap.c_str());
+    grids.readFrom(ifs);
+    dmap.readFrom(ifs);
+    AMREX_ALWAYS_ASSERT(S_old.boxArray().CellEqual(grids) && dmap == S_old.DistributionMap());
+    for (MFIter mfi(S_old); mfi.isValid(); ++mfi) {
+        std::ifstream ifc((f_chunk + std::to_string(mfi.index())).c_str());
+        S_old[mfi].readFrom(ifc); D_old[mfi].readFrom(ifc); S_new[mfi].readFrom(ifc);
+        hydro_src[mfi].readFrom(ifc); reset_src[mfi].readFrom(ifc); IR[mfi].readFrom(ifc);
+    }
+}
+}  // namespace
+#endif
+
+// HC/integrate_state_with_source_3d.cpp:50-185
 int Nyx::integrate_state_struct(MultiFab& S_old, MultiFab& S_new, MultiFab& D_old, MultiFab& hydro_src, MultiFab& IR, MultiFab& reset_src,
                                 const Real& a, const Real& a_end, const Real& delta_time, const int sdc_iter)
 {
     const long int store_steps = new_max_sundials_steps;
+#if !defined(NYX_HC_SHIM_BUILD)
+    {   // :82-125, same keys, same defaults, same order (write before read)
+        ParmParse pp_nyx("nyx");
+        long writeProc = ParallelDescriptor::IOProcessor() ? ParallelDescriptor::MyProc() : -1;
+        int hctest_example_write = 0, hctest_example_read = 0, hctest_example_index = 0, hctest_example_proc = 0;
+        pp_nyx.query("hctest_example_write", hctest_example_write);
+        if (pp_nyx.query("hctest_example_write_proc", writeProc)) hctest_example_proc = (ParallelDescriptor::MyProc() == writeProc);
+        else hctest_example_proc = 1;
+        if (hctest_example_write) hctest_example_index = nStep();
+        pp_nyx.query("hctest_example_index", hctest_example_index);
+        pp_nyx.query("hctest_example_read", hctest_example_read);
+        if (hctest_example_write != 0 || hctest_example_read != 0) {
+            std::string f_inputs = "hctest/inputs." + std::to_string(hctest_example_index);
+            std::string f_badmap = "hctest/BADMAP." + std::to_string(hctest_example_index);
+            std::string f_chunk = "hctest/Chunk." + std::to_string(hctest_example_index) + ".";
+            int directory_overwrite = pp_nyx.query("hctest_filename_inputs", f_inputs);
+            directory_overwrite += pp_nyx.query("hctest_filename_badmap", f_badmap);
+            directory_overwrite += pp_nyx.query("hctest_filename_chunk", f_chunk);
+            if (hctest_example_read == 0 && hctest_example_write != 0) {
+                if (directory_overwrite == 0) amrex::UtilCreateCleanDirectory("hctest", true);
+                else amrex::Print() << "Using the following paths for hctest:\n" << f_inputs << "\n" << f_badmap << "\n" << f_chunk << std::endl;
+            }
+            if (hctest_example_proc && hctest_example_write != 0) {
+                // nyx.hctest_endIndex = number of tiles of the reference's MFIter (a CVODE instance each there)
+                const auto tiling = (TilingIfNotGPU() && sundials_use_tiling) ? MFItInfo().EnableTiling(sundials_tile_size) : MFItInfo();
+                hctest_write(S_old, S_new, D_old, hydro_src, IR, reset_src, MFIter(S_old, tiling).length(), a, a_end, delta_time,
+                             hctest_example_index, f_inputs, f_badmap, f_chunk);
+            }
+            if (hctest_example_proc && hctest_example_read != 0) hctest_read(S_old, S_new, D_old, hydro_src, IR, reset_src, f_badmap, f_chunk);
+        }
+    }
+#endif
     std::vector<HcFab> f[6]; std::vector<HcBox> t;
     for (MFIter mfi(S_old); mfi.isValid(); ++mfi) {
         // C-ABI order == integrate_state_struct_mfin's: state, diag, state_n, hydro_src, reset_src, IR
@@ -170,7 +304,7 @@ int Nyx::integrate_state_struct(MultiFab& S_old, MultiFab& S_new, MultiFab& D_ol
         f[3].push_back(to_fab(hydro_src.array(mfi))); f[4].push_back(to_fab(reset_src.array(mfi))); f[5].push_back(to_fab(IR.array(mfi)));
         t.push_back(to_box(mfi.validbox()));
     }
-    return struct_batch(f, t, a, a_end, delta_time, sdc_iter, store_steps, new_max_sundials_steps);
+    return struct_batch(f, t, a, a_end, delta_time, sdc_iter, NYX_HC_FLAGS(), store_steps, new_max_sundials_steps);
 }
 
 // HC/integrate_state_with_source_3d.cpp:187-709: one tile
@@ -181,7 +315,7 @@ int Nyx::integrate_state_struct_mfin(Array4<Real> const& state4, Array4<Real> co
 {
     std::vector<HcFab> f[6] = {{to_fab(state4)}, {to_fab(diag_eos4)}, {to_fab(state_n4)}, {to_fab(hydro_src4)}, {to_fab(reset_src4)}, {to_fab(IR4)}};
     std::vector<HcBox> t{to_box(tbx)};
-    return struct_batch(f, t, a, a_end, delta_time, sdc_iter, old_max_steps, new_max_steps);
+    return struct_batch(f, t, a, a_end, delta_time, sdc_iter, NYX_HC_FLAGS(), old_max_steps, new_max_steps);
 }
 
 
@@ -196,7 +330,8 @@ void nyx_hc_compute_new_temp(MultiFab& S_new, MultiFab& D_new, Real a, Real smal
         s.push_back(to_fab(S_new.array(mfi))); d.push_back(to_fab(D_new.array(mfi))); t.push_back(to_box(mfi.validbox()));
     }
     if (t.empty()) return;
-    const HcParams p = params_from_nyx(Nyx::old_max_sundials_steps);
+    ensure_tables();
+    const HcParams p = eos_params();
     HcStats st{};
 #ifdef AMREX_USE_GPU
     check(hc_compute_new_temp_batch((int)t.size(), s.data(), d.data(), t.data(), a, &p, small_temp, large_temp, max_temp_dt, &st, nullptr));
@@ -214,7 +349,8 @@ void nyx_hc_reset_internal_energy(MultiFab& S_new, MultiFab& D_new, MultiFab& re
         t.push_back(to_box(mfi.validbox()));
     }
     if (t.empty()) return;
-    const HcParams p = params_from_nyx(Nyx::old_max_sundials_steps);
+    ensure_tables();
+    const HcParams p = eos_params();
 #ifdef AMREX_USE_GPU
     check(hc_reset_internal_energy_batch((int)t.size(), s.data(), d.data(), r.data(), t.data(), a, &p, small_temp, interp, nullptr));
 #else
@@ -230,30 +366,31 @@ void nyx_hc_reset_internal_energy(MultiFab& S_new, MultiFab& D_new, MultiFab& re
 // Nyx::typical_values_post_restart, Source/Driver/Nyx.cpp:1625-1657, which ParallelDescriptor::Bcast's them).  Same files, same quirk;
 // the caller broadcasts.
 #include <fstream>
-int nyx_hc_write_typical_steps(const std::string& dir)
+// (Nyx::old_max_sundials_steps / new_max_sundials_steps / use_typical_steps are protected statics: the calling Nyx members pass them)
+int nyx_hc_write_typical_steps(const std::string& dir, int use_typical_steps, long int old_max_sundials_steps)
 {
-    if (!Nyx::use_typical_steps) return 0;
+    if (!use_typical_steps) return 0;
     for (const char* fn : {"/first_max_steps", "/second_max_steps"}) {
         std::ofstream File((dir + fn).c_str(), std::ios::out | std::ios::trunc);
         if (!File.good()) return -1;
         File.precision(15);
-        File << Nyx::old_max_sundials_steps << '\n';
+        File << old_max_sundials_steps << '\n';
     }
     return 0;
 }
 
-int nyx_hc_read_typical_steps(const std::string& restart_file)
+int nyx_hc_read_typical_steps(const std::string& restart_file, int use_typical_steps, long int& old_max_sundials_steps, long int& new_max_sundials_steps)
 {
-    if (!Nyx::use_typical_steps) return 0;
+    if (!use_typical_steps) return 0;
     {
         std::ifstream File((restart_file + "/first_max_steps").c_str(), std::ios::in);
         if (!File.good()) return -1;
-        File >> Nyx::old_max_sundials_steps;
+        File >> old_max_sundials_steps;
     }
     {
         std::ifstream File((restart_file + "/second_max_steps").c_str(), std::ios::in);
         if (!File.good()) return -1;
-        File >> Nyx::new_max_sundials_steps;
+        File >> new_max_sundials_steps;
     }
     return 0;
 }

@@ -37,8 +37,8 @@ extern "C" const HcStats* nyx_hc_last_stats();
 void nyx_hc_compute_new_temp(MultiFab& S_new, MultiFab& D_new, Real a, Real small_temp, Real large_temp, int max_temp_dt);
 void nyx_hc_reset_internal_energy(MultiFab& S_new, MultiFab& D_new, MultiFab& reset_e_src, Real a, Real small_temp, int interp);
 extern "C" int nyx_hc_setup(const char* treecool_path, double mean_rhob);
-int nyx_hc_write_typical_steps(const std::string& dir);
-int nyx_hc_read_typical_steps(const std::string& restart_file);
+int nyx_hc_write_typical_steps(const std::string& dir, int use_typical_steps, long int old_max_sundials_steps);
+int nyx_hc_read_typical_steps(const std::string& restart_file, int use_typical_steps, long int& old_max_sundials_steps, long int& new_max_sundials_steps);
 
 extern "C" {
 
@@ -118,8 +118,10 @@ void nyxref_reset_internal_energy(const int* box, int ng_state, int ng_diag, int
     nyx_hc_reset_internal_energy(S, D, R, a, small_temp, interp);
 }
 
-int nyxref_write_typical_steps(const char* dir) { return nyx_hc_write_typical_steps(dir); }
-int nyxref_read_typical_steps(const char* dir) { return nyx_hc_read_typical_steps(dir); }
+int nyxref_write_typical_steps(const char* dir) { return nyx_hc_write_typical_steps(dir, Nyx::use_typical_steps, Nyx::old_max_sundials_steps); }
+int nyxref_read_typical_steps(const char* dir) {
+    return nyx_hc_read_typical_steps(dir, Nyx::use_typical_steps, Nyx::old_max_sundials_steps, Nyx::new_max_sundials_steps);
+}
 
 void nyxref_update_state_with_sources(int nboxes, const int* boxes, const int* ng, double* const* s_old, double* const* s_new,
                                       double* const* ext_src, double* const* hydro_src, double* const* grav, double* const* reset_src,

