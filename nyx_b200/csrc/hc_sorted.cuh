@@ -19,29 +19,10 @@
 
 namespace sorted {
 
-// ---- scalar fields of a lane kept in shared memory between phases (the Nordsieck arrays occupy slots 0..ARR_DOUBLES-1)
-#define HC_SD_COMMON(X) X(req_t) X(req_y) X(rho) X(e0) X(lastT) X(lastNe) X(ewt) X(acor) X(ftemp) X(tn) X(h) X(hprime) X(eta) X(hscale) \
-    X(etamax) X(rl1) X(gamma) X(gammap) X(crate) X(delp) X(saved_tq5) X(M) X(gammasv) X(saved_t) X(delta) X(yy_ft) X(hg) X(hub) X(hlb) X(e_final)
-// (outT, outNe, IR -- the SDC finalize results that wait for the final EOS solve when reionization heating is on -- have no slots of their
-//  own: a lane in PC_FINAL_EOS keeps them in the slots of the cvHin locals hg, hub, hlb, which are dead after the initial step.  592 instead
-//  of 616 bytes per lane: 384 instead of 352 lanes fit.)
-#if !defined(HC_STRUCT_ALIAS_OUT)
-#define HC_STRUCT_ALIAS_OUT 1
-#endif
-#if HC_STRUCT_ALIAS_OUT
-#define HC_SD_STRUCT(X) X(jh) X(rho_src) X(rhoe_src) X(e_src) X(rho_out) X(rhoe_new) X(reset_src) X(zhi) X(lastNh) X(lastRho) X(eos_nhe0) \
-    X(eos_nhepp)
-#else
-#define HC_SD_STRUCT(X) X(jh) X(rho_src) X(rhoe_src) X(e_src) X(rho_out) X(rhoe_new) X(reset_src) X(zhi) X(lastNh) X(lastRho) X(eos_nhe0) \
-    X(eos_nhepp) X(outT) X(outNe) X(IR)
-#endif
-#define HC_COUNT(name) +1
-constexpr int ND_COMMON = 0 HC_SD_COMMON(HC_COUNT);
-constexpr int ND_STRUCT = 0 HC_SD_STRUCT(HC_COUNT);
-template <int PATH> constexpr int nd_total() { return ARR_DOUBLES + ND_COMMON + (PATH == PATH_STRUCT ? ND_STRUCT : 0) + 1 /* fval */; }
-// 32-bit words per lane: two packed words of small integers, 12 counters, 4 words of cell coordinates
-#define HC_SI_WORDS(X) X(nst) X(nstlp) X(nfe) X(nfe_ls) X(netf) X(nni) X(nnf) X(nsetups) X(ne_iters) X(attempts) X(n_eos) X(flag)
-constexpr int NI_WORDS = 2 + (0 HC_SI_WORDS(HC_COUNT)) + 4;
+// The lane state between phases is what Lane::save() writes (hc_device.cuh, "persistence between rounds"): LaneT::ND doubles
+// (the 22 Nordsieck / coefficient doubles first) and LaneT::WS_N 32-bit words per lane, structure of arrays [slot][lane].
+// 364 bytes per lane on the Strang path, 420 on the SDC path: 384 lanes fit the 164 KB shared-memory carve-out, which leaves the L1 92 KB
+// for the rate tables and the stack (round 1: 496 / 592 bytes, 196 / 228 KB carve-out, 60 / 28 KB of L1).
 #if !defined(HC_SORT_FINE)
 #define HC_SORT_FINE 2
 #endif
@@ -68,9 +49,24 @@ __device__ __forceinline__ int key_class(int key) {
 #endif
 }
 
+template <int STRIDE>
+struct ArrSmemT {
+    double* p;   // this lane's slot 0
+    __device__ __forceinline__ double& at(int slot) const { return p[slot * STRIDE]; }
+};
+// slot access of one lane for Lane::save / load / load_request / save_result
+template <int STRIDE>
+struct SmemIO {
+    double* pd; unsigned* pw;
+    __device__ __forceinline__ double& d(int slot) const { return pd[slot * STRIDE]; }
+    __device__ __forceinline__ unsigned& w(int slot) const { return pw[slot * STRIDE]; }
+};
+
 template <int PATH, int LANES>
 struct Layout {
-    static constexpr int ND = nd_total<PATH>();
+    using LaneT = Lane<PATH, ArrSmemT<LANES>>;
+    static constexpr int ND = LaneT::ND;
+    static constexpr int NI_WORDS = LaneT::WS_N;
     static constexpr int WARPS = LANES / 32;
     static constexpr size_t bytes_d = (size_t)ND * LANES * sizeof(double);
     static constexpr size_t bytes_i = (size_t)NI_WORDS * LANES * sizeof(int);
@@ -78,12 +74,6 @@ struct Layout {
     static constexpr size_t bytes_cnt = (size_t)NKEY * WARPS * sizeof(int);
     static constexpr size_t total = bytes_d + bytes_i + bytes_order + bytes_cnt;
     static_assert((total + 2048) * HC_SORTED_CTAS <= 228 * 1024, "shared memory budget of one sm_100 SM");
-};
-
-template <int STRIDE>
-struct ArrSmemT {
-    double* p;   // this lane's slot 0
-    __device__ __forceinline__ double& at(int slot) const { return p[slot * STRIDE]; }
 };
 
 template <class LaneT>
@@ -114,21 +104,6 @@ __device__ __forceinline__ int sort_key(unsigned w0, unsigned w1) {
     }
 }
 
-template <class LaneT>
-__device__ __forceinline__ void pack_ints(const LaneT& ln, unsigned& w0, unsigned& w1) {
-    w0 = (unsigned)ln.pc | ((unsigned)ln.q << 4) | ((unsigned)ln.qprime << 8) | ((unsigned)ln.qwait << 12) | ((unsigned)ln.L << 16) |
-         ((unsigned)ln.ncf << 20) | ((unsigned)ln.nef << 24) | ((unsigned)ln.curiter << 28);
-    w1 = (unsigned)ln.nflag | ((unsigned)ln.hin_count << 4) | ((unsigned)ln.callSetup << 8) | ((unsigned)ln.res_at_top << 9) |
-         ((unsigned)ln.jcur << 10) | ((unsigned)ln.nls_jcur << 11) | ((unsigned)ln.floor_hit << 12);
-}
-template <class LaneT>
-__device__ __forceinline__ void unpack_ints(LaneT& ln, unsigned w0, unsigned w1) {
-    ln.pc = (int)(w0 & 15u); ln.q = (int)((w0 >> 4) & 15u); ln.qprime = (int)((w0 >> 8) & 15u); ln.qwait = (int)((w0 >> 12) & 15u);
-    ln.L = (int)((w0 >> 16) & 15u); ln.ncf = (int)((w0 >> 20) & 15u); ln.nef = (int)((w0 >> 24) & 15u); ln.curiter = (int)((w0 >> 28) & 15u);
-    ln.nflag = (int)(w1 & 15u); ln.hin_count = (int)((w1 >> 4) & 15u); ln.callSetup = (w1 >> 8) & 1u; ln.res_at_top = (w1 >> 9) & 1u;
-    ln.jcur = (w1 >> 10) & 1u; ln.nls_jcur = (w1 >> 11) & 1u; ln.floor_hit = (int)((w1 >> 12) & 1u);
-}
-
 #if defined(HC_PHASE_TIMING)
 // diagnostics build only: per-phase clock64 totals summed over warps: [0] rounds*warps [1] sort [2] B work [3] B barrier wait [4] R work [5] R barrier wait
 // [6] active lanes at R (sum over rounds) [7] kernel cycles*warps [8..15] lanes per sort key (sum over rounds)
@@ -143,10 +118,11 @@ __device__ unsigned long long g_phase[48];
 template <int PATH, int LANES>
 __global__ void __launch_bounds__(LANES, HC_SORTED_CTAS) hc_sorted_kernel(const __grid_constant__ KernelArgs a) {
     using L = Layout<PATH, LANES>;
-    using LaneT = Lane<PATH, ArrSmemT<LANES>>;
+    using LaneT = typename L::LaneT;
+    using IO = SmemIO<LANES>;
     __shared__ unsigned long long s_stats[S_COUNT];
     double* sd = reinterpret_cast<double*>(s_raw);
-    int* si = reinterpret_cast<int*>(s_raw + L::bytes_d);
+    unsigned* si = reinterpret_cast<unsigned*>(s_raw + L::bytes_d);
     unsigned short* s_order = reinterpret_cast<unsigned short*>(s_raw + L::bytes_d + L::bytes_i);
     int* s_cnt = reinterpret_cast<int*>(s_raw + L::bytes_d + L::bytes_i + L::bytes_order);   // [NKEY][WARPS] counts
 
@@ -156,15 +132,9 @@ __global__ void __launch_bounds__(LANES, HC_SORTED_CTAS) hc_sorted_kernel(const 
     const Tables tb{a.ionx, a.iony, a.cool, a.logtab};   // all three in global memory (L1/L2)
     const Consts& c = a.k;
 
-    // slot indices
-    enum : int { SD0 = ARR_DOUBLES };
-    constexpr int SD_FVAL = L::ND - 1;
-    enum : int { SI_W0 = 0, SI_W1 = 1, SI_CNT0 = 2, SI_TILE = NI_WORDS - 4, SI_CI = NI_WORDS - 3, SI_CJ = NI_WORDS - 2, SI_CK = NI_WORDS - 1 };
-
     if (tid < S_COUNT) s_stats[tid] = 0ull;
-    si[SI_W0 * LANES + tid] = PC_IDLE;
-    si[SI_W1 * LANES + tid] = 0;
-    sd[(SD0 + 1) * LANES + tid] = 200.0;   // req_y of an idle lane: never evaluated, but keep it benign
+    si[LaneT::WS_W0 * LANES + tid] = PC_IDLE;
+    si[LaneT::WS_W1 * LANES + tid] = 0u;
     Totals tot;
 #pragma unroll
     for (int i = 0; i < 7; ++i) tot.w[i] = 0ull;
@@ -183,7 +153,7 @@ __global__ void __launch_bounds__(LANES, HC_SORTED_CTAS) hc_sorted_kernel(const 
     for (;;) {
         // ================= phase S: stable counting sort of the lanes by integrator phase
         {
-            const int key = sort_key<LaneT>((unsigned)si[SI_W0 * LANES + tid], (unsigned)si[SI_W1 * LANES + tid]);
+            const int key = sort_key<LaneT>(si[LaneT::WS_W0 * LANES + tid], si[LaneT::WS_W1 * LANES + tid]);
             const unsigned same = __match_any_sync(0xffffffffu, key);
             const int rank = __popc(same & lt_mask);
             if (lane_id < NKEY) s_cnt[lane_id * L::WARPS + warp] = 0;
@@ -223,37 +193,24 @@ __global__ void __launch_bounds__(LANES, HC_SORTED_CTAS) hc_sorted_kernel(const 
         bool active_after;
         {
             const int my = s_order[tid];
+            const IO io{sd + my, si + my};
             LaneT ln;
             ln.arr.p = sd + my;
-            unsigned w0 = (unsigned)si[SI_W0 * LANES + my], w1 = (unsigned)si[SI_W1 * LANES + my];
-            unpack_ints(ln, w0, w1);
-            {
-                int s = SD0;
-#define HC_LD(name) ln.name = sd[(s++) * LANES + my];
-                HC_SD_COMMON(HC_LD)
-                if (PATH == PATH_STRUCT) { HC_SD_STRUCT(HC_LD) }
-#undef HC_LD
-#if HC_STRUCT_ALIAS_OUT
-                if (PATH == PATH_STRUCT) { ln.outT = ln.hg; ln.outNe = ln.hub; ln.IR = ln.hlb; }   // meaningful in PC_FINAL_EOS only
-#endif
-                int w = SI_CNT0;
-#define HC_LDI(name) ln.name = si[(w++) * LANES + my];
-                HC_SI_WORDS(HC_LDI)
-#undef HC_LDI
+            const unsigned w0_in = io.w(LaneT::WS_W0);
+            double f = 0.0;
+            // the lane's cell, packed: tile (20 bits) | k (12 bits), i (16) | j (16), relative to the tile.  Decoded only where the FABs
+            // are touched (finalize data, store of a finished cell): once per cell, not once per round
+            unsigned cell0 = 0u, cell1 = 0u;
+            ln.pc = (int)(w0_in & 15u);
+            if (ln.pc != PC_IDLE) {
+                ln.load(io, c, f);
+                cell0 = io.w(LaneT::WS_CELL0); cell1 = io.w(LaneT::WS_CELL1);
             }
-            if (PATH != PATH_STRUCT) {
-                ln.jh = 1.0; ln.rho_src = ln.rhoe_src = ln.e_src = ln.rho_out = ln.rhoe_new = ln.reset_src = ln.zhi = 0.0;
-                ln.lastNh = 1.0; ln.lastRho = ln.rho; ln.eos_nhe0 = ln.eos_nhepp = 0.0; ln.outT = ln.outNe = ln.IR = 0.0;
-            }
-            ln.abstol = nv_scale(c.atol_factor, ln.e0);
-            ln.y = 0.0; ln.gamrat = 0.0; ln.acnrm = 0.0;
-            int c_tile = si[SI_TILE * LANES + my], c_i = si[SI_CI * LANES + my], c_j = si[SI_CJ * LANES + my], c_k = si[SI_CK * LANES + my];
-            const double f = sd[SD_FVAL * LANES + my];
-
             HC_TICK(16);
 #if defined(HC_PHASE_TIMING)
             const long long t_b0 = clock64();
-            const int key0 = key_class(__shfl_sync(0xffffffffu, sort_key<LaneT>(w0, w1), 0));
+            const unsigned w1_in = io.w(LaneT::WS_W1);
+            const int key0 = key_class(__shfl_sync(0xffffffffu, sort_key<LaneT>(w0_in, w1_in), 0));
 #endif
             const bool act0 = ln.active();
             const unsigned rmask = __ballot_sync(0xffffffffu, act0);
@@ -261,12 +218,19 @@ __global__ void __launch_bounds__(LANES, HC_SORTED_CTAS) hc_sorted_kernel(const 
 #if !defined(HC_DBG_CLASS)
 #define HC_DBG_CLASS 2   // 0: Newton-residual lanes, 2: Jacobian-setup lanes
 #endif
-            ln.dbg_on = (key0 == HC_DBG_CLASS) && (key_class(__shfl_sync(0xffffffffu, sort_key<LaneT>(w0, w1), 31)) == HC_DBG_CLASS);   // stage timing: warps made of one phase only
+            ln.dbg_on = (key0 == HC_DBG_CLASS) && (key_class(__shfl_sync(0xffffffffu, sort_key<LaneT>(w0_in, w1_in), 31)) == HC_DBG_CLASS);   // stage timing: warps made of one phase only
             ln.dbg_last = clock64();
 #endif
             if (act0) {
+                // (SDC path) the cell data only the finalize step reads is fetched again when a lane gets there: it is not part of the lane state
+                if (PATH == PATH_STRUCT && ln.pc == PC_FINAL_EOS) load_finalize_cell(ln, a, cell0, cell1);
                 ln.resume(c, f, rmask);
-                if (!ln.active()) store_cell(ln, a, a.tiles[c_tile], c_i, c_j, c_k, tot);
+                if (ln.fin_pending) {
+                    if (PATH == PATH_STRUCT) load_finalize_cell(ln, a, cell0, cell1);
+                    ln.begin_finalize(c);
+                }
+                tot.w[5] += (unsigned long long)(unsigned)ln.attempts << 32;
+                if (!ln.active()) store_cell_packed(ln, a, cell0, cell1, tot);
             }
             __syncwarp();
             HC_TICK(17);
@@ -293,10 +257,14 @@ __global__ void __launch_bounds__(LANES, HC_SORTED_CTAS) hc_sorted_kernel(const 
                     const int avail = w_xend - w_x;
                     const int rk = __popc(m & lt_mask);
                     if (need && rk < avail) {
-                        c_tile = w_tile; c_i = w_x + rk; c_j = w_j; c_k = w_k;
-                        load_cell(ln, a, a.tiles[c_tile], c_i, c_j, c_k);
-                        if (ln.active()) need = false;
-                        else store_cell(ln, a, a.tiles[c_tile], c_i, c_j, c_k, tot);
+                        const TileDesc& t = a.tiles[w_tile];
+                        const int c_i = w_x + rk;
+                        cell0 = ((unsigned)w_tile << 12) | (unsigned)(w_k - t.lo[2]);
+                        cell1 = ((unsigned)(c_i - t.lo[0]) << 16) | (unsigned)(w_j - t.lo[1]);
+                        load_cell(ln, a, t, c_i, w_j, w_k);
+                        tot.w[5] += (unsigned long long)(unsigned)ln.attempts << 32;
+                        if (ln.active()) { need = false; io.w(LaneT::WS_CELL0) = cell0; io.w(LaneT::WS_CELL1) = cell1; }
+                        else store_cell(ln, a, t, c_i, w_j, w_k, tot);
                     }
                     w_x += min(avail, __popc(m));
                     m = __ballot_sync(0xffffffffu, need);
@@ -304,24 +272,11 @@ __global__ void __launch_bounds__(LANES, HC_SORTED_CTAS) hc_sorted_kernel(const 
             }
             HC_TICK(18);
             // ---- write the lane back
-            pack_ints(ln, w0, w1);
-            si[SI_W0 * LANES + my] = (int)w0; si[SI_W1 * LANES + my] = (int)w1;
-            {
-#if HC_STRUCT_ALIAS_OUT
-                if (PATH == PATH_STRUCT && ln.pc == PC_FINAL_EOS) { ln.hg = ln.outT; ln.hub = ln.outNe; ln.hlb = ln.IR; }
-#endif
-                int s = SD0;
-#define HC_ST(name) sd[(s++) * LANES + my] = ln.name;
-                HC_SD_COMMON(HC_ST)
-                if (PATH == PATH_STRUCT) { HC_SD_STRUCT(HC_ST) }
-#undef HC_ST
-                int w = SI_CNT0;
-#define HC_STI(name) si[(w++) * LANES + my] = ln.name;
-                HC_SI_WORDS(HC_STI)
-#undef HC_STI
-            }
-            si[SI_TILE * LANES + my] = c_tile; si[SI_CI * LANES + my] = c_i; si[SI_CJ * LANES + my] = c_j; si[SI_CK * LANES + my] = c_k;
             active_after = ln.active();
+            if (active_after) ln.save(io);
+            else {
+                io.w(LaneT::WS_W0) = PC_IDLE; io.w(LaneT::WS_W1) = 0u;
+            }
 #if defined(HC_PHASE_TIMING)
             {
                 const long long t_b1 = clock64();
@@ -338,34 +293,17 @@ __global__ void __launch_bounds__(LANES, HC_SORTED_CTAS) hc_sorted_kernel(const 
 
         // ================= phase R: thread t evaluates the request of lane t
         {
+            const IO io{sd + tid, si + tid};
             LaneT ln;
             ln.arr.p = sd + tid;
-            ln.pc = (int)((unsigned)si[SI_W0 * LANES + tid] & 15u);
+            ln.pc = (int)(io.w(LaneT::WS_W0) & 15u);
             if (ln.active()) {
-                ln.req_t = sd[(SD0 + 0) * LANES + tid];
-                ln.req_y = sd[(SD0 + 1) * LANES + tid];
-                ln.rho = sd[(SD0 + 2) * LANES + tid];
-                ln.ne_iters = 0; ln.n_eos = 0;
-                ln.jh = 1.0; ln.rho_src = 0.0; ln.e_src = 0.0; ln.lastRho = ln.rho;
-                if (PATH == PATH_STRUCT) {
-                    constexpr int S0 = SD0 + ND_COMMON;   // order of HC_SD_STRUCT: jh rho_src rhoe_src e_src ... lastNh(8) lastRho(9) eos_nhe0(10) eos_nhepp(11)
-                    ln.jh = sd[(S0 + 0) * LANES + tid]; ln.rho_src = sd[(S0 + 1) * LANES + tid]; ln.e_src = sd[(S0 + 3) * LANES + tid];
-                    ln.lastRho = sd[(S0 + 9) * LANES + tid];
-                }
+                ln.load_request(io);
                 const bool is_eos = (ln.pc == PC_FINAL_EOS);
                 const double f = ln.eval_request(tb, c);
-                sd[SD_FVAL * LANES + tid] = f;
-                sd[(SD0 + 1) * LANES + tid] = ln.req_y;                 // the RHS clamps its argument in place (f_rhs.H:167)
-                sd[(SD0 + 4) * LANES + tid] = ln.lastT;
-                sd[(SD0 + 5) * LANES + tid] = ln.lastNe;
-                if (PATH == PATH_STRUCT) {
-                    constexpr int S0 = SD0 + ND_COMMON;
-                    if (is_eos) { sd[(S0 + 10) * LANES + tid] = ln.eos_nhe0; sd[(S0 + 11) * LANES + tid] = ln.eos_nhepp; }
-                    else { sd[(S0 + 8) * LANES + tid] = ln.lastNh; sd[(S0 + 9) * LANES + tid] = ln.lastRho; }
-                }
-                // counters: ne_iters is word 8, n_eos word 10 of HC_SI_WORDS
-                si[(SI_CNT0 + 8) * LANES + tid] += ln.ne_iters;
-                si[(SI_CNT0 + 10) * LANES + tid] += ln.n_eos;
+                ln.save_result(io, f, is_eos);
+                tot.w[5] += (unsigned long long)(unsigned)ln.ne_iters;
+                tot.w[6] += (unsigned long long)(unsigned)ln.n_eos;
             }
 #if defined(HC_PHASE_TIMING)
             ph[6] += ln.active() ? 1 : 0;

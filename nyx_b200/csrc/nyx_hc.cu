@@ -1,17 +1,18 @@
 // nyx_hc.cu -- sm_100a kernels and the C-ABI of include/nyx_hc.h.
 //
 // Kernel design (DESIGN.md has the numbers):
-//   * one persistent CTA per SM, 227 KB-class shared memory: the 7 ionization-rate tables (read ~6x per RHS
-//     evaluation) are staged interleaved in shared memory, one 64-byte row per temperature index, so one lookup
-//     is two adjacent rows = 128 contiguous bytes; the 8 cooling tables (read once per RHS) stay in L1/L2 (__ldg);
-//     the UV-background row is interpolated once per call on the host (z is uniform) and travels as kernel constants;
-//   * one thread (lane) per cell in flight, CVODE-equivalent BDF state in registers (hc_device.cuh);
-//   * a global work queue of cells: a lane that finishes its cell immediately pulls the next one
-//     (warp-aggregated atomicAdd on ballot of free lanes), and the integrator is a resumable state machine so that
-//     the 32 lanes of a warp evaluate their right-hand sides together whatever BDF phase each is in;
-//   * per-cell outputs are scattered straight to the FABs; diagnostics are reduced in shared memory, then one
-//     atomicAdd per CTA per counter.
-// No AMReX, no SUNDIALS, no library kernels.
+//   * the integrator kernel is sorted::hc_sorted_kernel (hc_sorted.cuh): one persistent CTA of 384 threads per SM; the whole integrator
+//     state of the 384 cells in flight lives in SHARED MEMORY (364 / 420 bytes per lane, structure of arrays), and every round has three
+//     CTA-wide phases -- R: thread t evaluates the pending right-hand side / EOS request of lane t (the FP64-heavy part, full warps);
+//     S: the lanes are counting-sorted by integrator phase; B: thread t runs the CVODE bookkeeping of lane order[t] (hc_device.cuh:
+//     a resumable per-cell BDF state machine), stores finished cells and refills idle lanes from a global work queue of x-row pieces;
+//   * the rate tables stay in global memory behind the L1 (92 KB next to the 164 KB shared-memory carve-out) and L2; the rows of one
+//     temperature bin are cached in registers across the evaluation points of an ionization-equilibrium solve; the UV-background row is
+//     interpolated once per call on the host (z is uniform) and travels as kernel constants;
+//   * per-cell outputs are scattered straight to the FABs; diagnostics are per-thread totals, reduced once at kernel end;
+//   * hc_eos_kernel (compute_new_temp / EOS rows: one ionization-equilibrium solve per cell, tables staged in shared memory) and the
+//     streaming kernels of the rows either side of the path (hc_reset_e_kernel, hc_sources.cuh) follow.
+// No AMReX, no SUNDIALS, no library kernels, no CPU fallback.
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -25,48 +26,15 @@
 #include <mutex>
 #include <vector>
 
-// Build-time tuning knobs (measured on B200, profiles/): 384 lanes per SM leave 168 registers per lane (the integrator state
-// stays in registers), and the CTA-wide phase lock keeps one phase's code in the small instruction caches at a time.
-#ifndef HC_ARCH
-#define HC_ARCH 2                          // 1: register-resident lanes (hc_integrate_kernel); 2: phase-sorted lanes in shared memory (hc_sorted.cuh)
-#endif
-#ifndef HC_LOCKSTEP
-#define HC_LOCKSTEP 1                      // 0: warps free-run; 1: CTA-wide RHS / bookkeeping phase lock; 2: per-scheduler warp groups in lockstep
-#endif
-#ifndef HC_THREADS
-#define HC_THREADS 384                     // lanes (cells in flight) per SM; one persistent CTA per SM
-#endif
+// Build-time tuning knobs (measured on B200, profiles/): 384 lanes per SM leave 168 registers per thread
 #ifndef HC_SORTED_LANES_VEC
-#define HC_SORTED_LANES_VEC 384            // HC_ARCH 2: 496 B of shared memory per lane on the Strang path
+#define HC_SORTED_LANES_VEC 384            // lanes (cells in flight) per SM, one persistent CTA per SM; 364 B of shared memory per lane on the Strang path
 #endif
 #ifndef HC_SORTED_CTAS
-#define HC_SORTED_CTAS 1                   // HC_ARCH 2: CTAs per SM (each with its own phase barriers; LANES x CTAS lanes in flight per SM)
+#define HC_SORTED_CTAS 1                   // CTAs per SM (each with its own phase barriers; LANES x CTAS lanes in flight per SM)
 #endif
 #ifndef HC_SORTED_LANES_STRUCT
-#define HC_SORTED_LANES_STRUCT 384         // 592 B per lane on the SDC path (outT, outNe, IR share the slots of the cvHin locals): measured against 320 lanes over the
-                                           // config-5 redshift sweep (flash reionization, 256^3): 927.8 ms against 1013.9 ms summed over z = 6 ... 2, faster at every z
-#endif
-#if HC_LOCKSTEP == 2
-// SMSP-group lockstep: the warps that share a scheduler (warp id mod 4) -- and with it an L0 instruction cache -- step through
-// the RHS evaluation points and the bookkeeping stages together, synchronised by a named barrier per group.
-__host__ __device__ __forceinline__ void hc_group_sync() {
-#if defined(__CUDA_ARCH__)
-    asm volatile("bar.sync %0, %1;" ::"r"(1 + (int)((threadIdx.x >> 5) & 3u)), "r"(HC_THREADS / 4) : "memory");
-#endif
-}
-__host__ __device__ __forceinline__ bool hc_group_all(bool pred) {
-#if defined(__CUDA_ARCH__)
-    int r;
-    asm volatile("{ .reg .pred p, q; setp.ne.s32 q, %3, 0; bar.red.and.pred p, %1, %2, q; selp.s32 %0, 1, 0, p; }"
-                 : "=r"(r) : "r"(1 + (int)((threadIdx.x >> 5) & 3u)), "r"(HC_THREADS / 4), "r"((int)pred) : "memory");
-    return r != 0;
-#else
-    return pred;
-#endif
-}
-#define HC_STAGE_SYNC(mask, act) do { hc_group_sync(); asm volatile("" : "+r"(act)); } while (0)
-#define HC_GROUP_ALL(pred) hc_group_all(pred)
-#define HC_GROUP_RHS 1
+#define HC_SORTED_LANES_STRUCT 384         // 420 B per lane on the SDC path
 #endif
 #if defined(HC_PHASE_TIMING)
 // diagnostics build: cycles between the stage boundaries of Lane::resume(), summed over the warps the kernel switches on
@@ -84,28 +52,19 @@ namespace {
 
 using namespace hc;
 
-constexpr int THREADS = HC_THREADS;
 #ifndef HC_EOS_THREADS
 #define HC_EOS_THREADS 512                 // threads per CTA of hc_eos_kernel, one CTA per SM (tables: 112 KB of shared memory); measured 256: 6.9, 384: 5.5, 512: 4.9, 768: 4.9 ms per 3.4e7 cells
 #endif
 constexpr int EOS_THREADS = HC_EOS_THREADS;
 constexpr int TAB_ROWS = NTAB + 1;         // one padding row: row j+1 always exists
 constexpr int CHUNK_MAX = 256;             // cells per work-queue chunk (a piece of one x-row of a tile)
-// dynamic shared memory: [ionx 2002 x 48 B][iony 2003 x 8 B, padded to 16][lane arrays ARR_DOUBLES x THREADS x 8 B]
+// dynamic shared memory of hc_eos_kernel: [ionx 2002 x 48 B][iony 2003 x 8 B, padded to 16]
 constexpr size_t SM_IONX = (size_t)TAB_ROWS * IONX_ROW * sizeof(double);
 constexpr size_t SM_IONY = (((size_t)TAB_ROWS + 1) * sizeof(double) + 15) / 16 * 16;
-constexpr size_t SM_ARR = (size_t)ARR_DOUBLES * THREADS * sizeof(double);
-constexpr size_t SMEM_INTEGRATE = SM_IONX + SM_IONY + SM_ARR;
 constexpr size_t SMEM_EOS = SM_IONX + SM_IONY;
-static_assert(SMEM_INTEGRATE <= 227 * 1024, "shared memory budget of one sm_100 CTA");
 
-// dynamic shared memory of both kernels, and the lanes' array storage inside it (slot-major, lane-minor: conflict-free)
+// dynamic shared memory of the kernels
 extern __shared__ __align__(16) unsigned char s_raw[];
-struct ArrSmem {
-    double* p;   // this lane's slot 0
-    __device__ __forceinline__ double& at(int slot) const { return p[slot * THREADS]; }
-};
-template <int PATH> using KLane = Lane<PATH, ArrSmem>;
 
 enum Comp { DENS = 0, EDEN = 4, EINT = 5, TEMP = 0, NE = 1, ZHI = 2 };
 enum FabSlot { F_STATE = 0, F_DIAG = 1, F_SNEW = 2, F_HSRC = 3, F_RSRC = 4, F_IR = 5 };
@@ -205,7 +164,6 @@ __device__ __forceinline__ void load_cell(LaneT& ln, const KernelArgs& a, const 
     const double rhoe0 = t.f[F_STATE].p[so + EINT * t.f[F_STATE].nstride];
     ln.e0 = rhoe0 / ln.rho;
     ln.abstol = nv_scale(c.atol_factor, ln.e0);
-    ln.lastNh = 1.0;
     ln.jh = (double)c.JH0;
     if (PATH == PATH_STRUCT) {
         const long long dof = fab_off(t.f[F_DIAG], i, j, k);
@@ -227,6 +185,29 @@ __device__ __forceinline__ void load_cell(LaneT& ln, const KernelArgs& a, const 
         ln.lastT = 0.0; ln.lastNe = 0.0;   // diag(Temp, Ne) are dead inputs on the Strang path (always overwritten, eos_hc.H:151)
     }
     ln.start(c);
+}
+
+// (SDC path) the cell data only the finalize step reads -- rhoe_src, reset_src of the source construction and S_new(rho, rho e) -- is not
+// part of the lane state between rounds: a lane that reaches ode_eos_finalize_struct fetches it again (once per cell)
+__device__ __forceinline__ void unpack_cell(const KernelArgs& a, unsigned cell0, unsigned cell1, int& tile, int& i, int& j, int& k) {
+    tile = (int)(cell0 >> 12);
+    const TileDesc& t = a.tiles[tile];
+    k = t.lo[2] + (int)(cell0 & 0xfffu); i = t.lo[0] + (int)(cell1 >> 16); j = t.lo[1] + (int)(cell1 & 0xffffu);
+}
+template <class LaneT>
+__device__ __forceinline__ void load_finalize_cell(LaneT& ln, const KernelArgs& a, unsigned cell0, unsigned cell1) {
+    const Consts& c = a.k;
+    int tile, i, j, k;
+    unpack_cell(a, cell0, cell1, tile, i, j, k);
+    const TileDesc& t = a.tiles[tile];
+    ln.rhoe_src = 0.0; ln.reset_src = 0.0;
+    if (c.sdc_has_src) {
+        ln.rhoe_src = t.f[F_HSRC].p[fab_off(t.f[F_HSRC], i, j, k) + EINT * t.f[F_HSRC].nstride] / c.dt;
+        ln.reset_src = t.f[F_RSRC].p[fab_off(t.f[F_RSRC], i, j, k)];
+    }
+    const long long no = fab_off(t.f[F_SNEW], i, j, k);
+    ln.rho_out = t.f[F_SNEW].p[no + DENS * t.f[F_SNEW].nstride];
+    ln.rhoe_new = t.f[F_SNEW].p[no + EINT * t.f[F_SNEW].nstride];
 }
 
 // scatter a finished cell (HOT LOOP C: integrate_state_vec_3d.cpp:317-321, f_rhs_struct.H:290-291,438-444)
@@ -258,9 +239,15 @@ __device__ __forceinline__ void store_cell(const LaneT& ln, const KernelArgs& a,
     tot.w[2] += (unsigned long long)(unsigned)ln.nfe | ((unsigned long long)(unsigned)ln.nfe_ls << 32);
     tot.w[3] += (unsigned long long)(unsigned)ln.netf | ((unsigned long long)(unsigned)ln.nni << 32);
     tot.w[4] += (unsigned long long)(unsigned)ln.nnf | ((unsigned long long)(unsigned)ln.nsetups << 32);
-    tot.w[5] += (unsigned long long)(unsigned)ln.ne_iters | ((unsigned long long)(unsigned)ln.attempts << 32);
-    tot.w[6] += (unsigned long long)(unsigned)ln.n_eos;
+    // (ne_iters, attempts and n_eos go to the totals round by round: they are not part of the lane state)
     tot.max_nst = max(tot.max_nst, (unsigned)ln.nst);
+}
+
+template <class LaneT>
+__device__ __forceinline__ void store_cell_packed(const LaneT& ln, const KernelArgs& a, unsigned cell0, unsigned cell1, Totals& tot) {
+    int tile, i, j, k;
+    unpack_cell(a, cell0, cell1, tile, i, j, k);
+    store_cell(ln, a, a.tiles[tile], i, j, k, tot);
 }
 
 __device__ __noinline__ void flush_totals(const Totals& tot, unsigned long long* s_stats, unsigned long long* dstats) {
@@ -279,103 +266,6 @@ __device__ __noinline__ void flush_totals(const Totals& tot, unsigned long long*
         if (threadIdx.x == S_MAXNST) atomicMax(&dstats[threadIdx.x], s_stats[threadIdx.x]);
         else atomicAdd(&dstats[threadIdx.x], s_stats[threadIdx.x]);
     }
-}
-
-template <int PATH>
-__global__ void __launch_bounds__(THREADS, 1) hc_integrate_kernel(const __grid_constant__ KernelArgs a) {
-    __shared__ unsigned long long s_stats[S_COUNT];
-    double* s_ionx = reinterpret_cast<double*>(s_raw);
-    double* s_iony = reinterpret_cast<double*>(s_raw + SM_IONX);
-
-    stage_tables(a, s_ionx, s_iony);
-    if (threadIdx.x < S_COUNT) s_stats[threadIdx.x] = 0ull;
-    __syncthreads();
-
-    const Tables tb{s_ionx, s_iony, a.cool, a.logtab};
-    const unsigned lane_id = threadIdx.x & 31u;
-    const unsigned lt_mask = (1u << lane_id) - 1u;
-
-    KLane<PATH> ln;
-    ln.pc = PC_IDLE;
-    ln.rho = 1.0e10; ln.req_y = 200.0; ln.req_t = 0.0; ln.jh = 1.0; ln.rho_src = 0.0; ln.e_src = 0.0; ln.lastRho = 1.0e10;   // benign idle request
-    ln.arr.p = reinterpret_cast<double*>(s_raw + SM_IONX + SM_IONY) + threadIdx.x;
-    Totals tot;
-#pragma unroll
-    for (int i = 0; i < 7; ++i) tot.w[i] = 0ull;
-    tot.max_nst = 0u;
-
-    // the warp's current chunk (warp-uniform) and the lane's current cell
-    int w_tile = 0, w_j = 0, w_k = 0, w_x = 0, w_xend = 0;
-    int c_tile = 0, c_i = 0, c_j = 0, c_k = 0;
-    bool queue_empty = false;
-
-    for (;;) {
-        // ---- refill free lanes from the warp's chunk; pull a new chunk from the global queue when it is used up
-        if (!queue_empty) {
-            bool need = !ln.active();
-            unsigned m = __ballot_sync(0xffffffffu, need);
-            while (m) {
-                if (w_x >= w_xend) {
-                    unsigned long long chunk = 0;
-                    if (lane_id == 0) chunk = atomicAdd(a.queue, 1ull);
-                    chunk = __shfl_sync(0xffffffffu, chunk, 0);
-                    if (chunk >= (unsigned long long)a.nchunks) { queue_empty = true; break; }
-                    w_tile = find_tile_by_chunk(a.tiles, a.ntiles, (long long)chunk);
-                    const TileDesc& t = a.tiles[w_tile];
-                    const unsigned local = (unsigned)((long long)chunk - t.chunk_begin);
-                    const unsigned row = local / (unsigned)t.cpr, piece = local - row * (unsigned)t.cpr;
-                    const unsigned kk = row / (unsigned)t.ny;
-                    w_k = t.lo[2] + (int)kk;
-                    w_j = t.lo[1] + (int)(row - kk * (unsigned)t.ny);
-                    w_x = t.lo[0] + (int)piece * t.chunk_len;
-                    w_xend = min(w_x + t.chunk_len, t.lo[0] + t.nx);
-                }
-                const int avail = w_xend - w_x;
-                const int rank = __popc(m & lt_mask);
-                if (need && rank < avail) {
-                    c_tile = w_tile; c_i = w_x + rank; c_j = w_j; c_k = w_k;
-                    load_cell(ln, a, a.tiles[c_tile], c_i, c_j, c_k);
-                    // a cell whose integration cannot even start (illegal input) may be finished already: store it, stay free
-                    if (ln.active()) need = false;
-                    else store_cell(ln, a, a.tiles[c_tile], c_i, c_j, c_k, tot);
-                }
-                w_x += min(avail, __popc(m));
-                m = __ballot_sync(0xffffffffu, need);
-            }
-        }
-        const bool act0 = ln.active();
-#if HC_LOCKSTEP
-        // CTA-wide phase lock: all warps of the SM run the RHS code together, then the bookkeeping code together, so that
-        // the instruction caches hold one phase's code at a time
-        if (!__syncthreads_or(act0)) break;
-#else
-        if (!__any_sync(0xffffffffu, act0)) break;   // nothing in flight and the refill found the queue empty
-#endif
-
-        // ---- all lanes evaluate their pending request together
-        double f = 0.0;
-#if HC_LOCKSTEP == 2
-        f = ln.eval_request(tb, a.k);          // idle lanes evaluate a benign request: every lane takes part in the group barriers
-        ln.resume(a.k, f, 0xffffffffu);        // (an idle lane falls through all stages)
-        if (act0 && !ln.active()) store_cell(ln, a, a.tiles[c_tile], c_i, c_j, c_k, tot);
-#else
-        if (act0) f = ln.eval_request(tb, a.k);
-#if HC_LOCKSTEP
-        __syncthreads();
-#else
-        __syncwarp();
-#endif
-        // ---- integrator bookkeeping until the next request (staged, see hc_device.cuh)
-        const unsigned rmask = __ballot_sync(0xffffffffu, act0);
-        if (act0) {
-            ln.resume(a.k, f, rmask);
-            if (!ln.active()) store_cell(ln, a, a.tiles[c_tile], c_i, c_j, c_k, tot);
-        }
-#endif
-        __syncwarp();
-    }
-
-    flush_totals(tot, s_stats, a.dstats);
 }
 
 // EOS kernel: one thread per cell, grid-stride over the cells of all tiles; ionization tables staged in shared memory.
@@ -672,6 +562,12 @@ template <typename KernelT>
 int set_smem_attr(KernelT kernel, DeviceTables& dt, int slot, size_t bytes) {
     if (!dt.attr_set[slot]) {
         CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        // ask for the smallest shared-memory carve-out that holds one CTA (+ the 1 KB the system reserves + static): the rest of the 256 KB
+        // is L1 for the rate tables (carve-out steps ... 132, 164, 196, 228 KB)
+        static const int knob = [] { const char* e = std::getenv("NYX_HC_CARVEOUT_KB"); return e ? std::atoi(e) : 0; }();
+        const int want_kb = knob > 0 ? knob : (int)((bytes + 4096 + 1023) / 1024);
+        const int pct = std::min(100, (want_kb * 100 + 227) / 228);
+        CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
         dt.attr_set[slot] = true;
     }
     return HC_OK;
@@ -697,10 +593,15 @@ int launch(int path, int ntiles, const HcFab* const* fabs, int nf, const HcBox* 
         TileDesc td = make_tile(fabs, nf, t, tiles[t], ncells, nchunks);
         if (td.nx <= 0 || td.ny <= 0 || td.nz <= 0) continue;   // empty tile: nothing to do (as an empty MFIter tile)
         if (!tile_inside(td, nf)) { set_err("tile %d is not contained in its FABs (or a FAB pointer is null)", t); return HC_ERR_ARG; }
+        // a lane remembers its cell as (tile: 20 bits, k: 12 bits, i, j: 16 bits each, relative to the tile)
+        if ((path == PATH_VEC || path == PATH_STRUCT) && (td.nx > 65536 || td.ny > 65536 || td.nz > 4096 || h_tiles.size() >= (1u << 20))) {
+            set_err("tile %d: the integrator kernels take tiles of at most 65536 x 65536 x 4096 cells and at most 2^20 tiles per call", t); return HC_ERR_ARG;
+        }
         ncells += (long long)td.nx * td.ny * td.nz;
         nchunks += (long long)td.cpr * td.ny * td.nz;
         h_tiles.push_back(td);
     }
+    if (k.max_steps > 65535) { set_err("max_steps > 65535 (the step counters of a lane are 16-bit; CVodeSetMaxNumSteps is 2000 in Nyx)"); return HC_ERR_ARG; }
     if (stats) std::memset(stats, 0, sizeof *stats);
     if (ncells == 0) return HC_OK;
 
@@ -723,9 +624,6 @@ int launch(int path, int ntiles, const HcFab* const* fabs, int nf, const HcBox* 
     a.ionx = dt.ionx; a.iony = dt.iony; a.cool = dt.cool; a.logtab = dt.logtab;
     if (eos) { a.eos_mode = eos->mode; a.max_temp_dt = eos->max_temp_dt; a.interp = eos->interp; a.small_temp = eos->small_temp; a.large_temp = eos->large_temp; }
 
-    const long long want = (ncells + THREADS - 1) / THREADS;
-    const int grid = (int)std::min<long long>(want, dt.sm_count);
-#if HC_ARCH == 2
     constexpr int LV = HC_SORTED_LANES_VEC, LS = HC_SORTED_LANES_STRUCT;
     if (path == PATH_VEC) {
         const int g = (int)std::min<long long>((ncells + LV - 1) / LV, (long long)dt.sm_count * HC_SORTED_CTAS);
@@ -736,15 +634,6 @@ int launch(int path, int ntiles, const HcFab* const* fabs, int nf, const HcBox* 
         if (int rc = set_smem_attr(sorted::hc_sorted_kernel<PATH_STRUCT, LS>, dt, 1, sorted::Layout<PATH_STRUCT, LS>::total)) return rc;
         sorted::hc_sorted_kernel<PATH_STRUCT, LS><<<g, LS, sorted::Layout<PATH_STRUCT, LS>::total, stream>>>(a);
     } else {
-#else
-    if (path == PATH_VEC) {
-        if (int rc = set_smem_attr(hc_integrate_kernel<PATH_VEC>, dt, 0, SMEM_INTEGRATE)) return rc;
-        hc_integrate_kernel<PATH_VEC><<<grid, THREADS, SMEM_INTEGRATE, stream>>>(a);
-    } else if (path == PATH_STRUCT) {
-        if (int rc = set_smem_attr(hc_integrate_kernel<PATH_STRUCT>, dt, 1, SMEM_INTEGRATE)) return rc;
-        hc_integrate_kernel<PATH_STRUCT><<<grid, THREADS, SMEM_INTEGRATE, stream>>>(a);
-    } else {
-#endif
         if (path == PATH_RESET_E) {
             const int g = stream_grid(ncells, 1024, dt.sm_count);
             hc_reset_e_kernel<<<g, 256, 0, stream>>>(a);

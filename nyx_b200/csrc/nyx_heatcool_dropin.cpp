@@ -290,7 +290,9 @@ int Nyx::integrate_state_struct(MultiFab& S_old, MultiFab& S_new, MultiFab& D_ol
             if (hctest_example_proc && hctest_example_write != 0) {
                 // nyx.hctest_endIndex = number of tiles of the reference's MFIter (a CVODE instance each there)
                 const auto tiling = (TilingIfNotGPU() && sundials_use_tiling) ? MFItInfo().EnableTiling(sundials_tile_size) : MFItInfo();
-                hctest_write(S_old, S_new, D_old, hydro_src, IR, reset_src, MFIter(S_old, tiling).length(), a, a_end, delta_time,
+                int n_tiles = 0;
+                { MFIter mfi(S_old, tiling); n_tiles = mfi.length(); }   // (its own scope: AMReX allows one active MFIter at a time)
+                hctest_write(S_old, S_new, D_old, hydro_src, IR, reset_src, n_tiles, a, a_end, delta_time,
                              hctest_example_index, f_inputs, f_badmap, f_chunk);
             }
             if (hctest_example_proc && hctest_example_read != 0) hctest_read(S_old, S_new, D_old, hydro_src, IR, reset_src, f_badmap, f_chunk);

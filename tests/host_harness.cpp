@@ -2,6 +2,7 @@
 // the HOST, one lane at a time, so that its control flow and arithmetic can be compared bit-for-bit with the
 // oracle in a container without a GPU. The product itself never runs this path (no CPU fallback): the C-ABI
 // library only launches the CUDA kernels.
+#include <cstring>
 #include <vector>
 
 #include "../nyx_b200/csrc/hc_host.hpp"
@@ -19,6 +20,38 @@ struct View {
     double& operator()(int i, int j, int k, int n) const { return p[(i - lo[0]) + (j - lo[1]) * js + (k - lo[2]) * ks + n * ns]; }
 };
 View view(const HcFab* f) { return View{f->p, f->jstride, f->kstride, f->nstride, {f->lo[0], f->lo[1], f->lo[2]}}; }
+// the persistent slots of a lane between rounds (shared memory in the kernel)
+struct HostIO {
+    double dd[64]; unsigned ww[16];
+    double& d(int s) { return dd[s]; }
+    unsigned& w(int s) { return ww[s]; }
+};
+// One cell through the ROUND structure of the kernel: after every resume() the lane is saved to its slots, every transient member is
+// destroyed (all-ones bytes: NaNs / garbage), the evaluation phase works on its own view of the slots, and the bookkeeping phase reloads
+// the lane.  Any state the kernel would lose between rounds is lost here too.
+template <class LaneT, class Fetch>
+void run_cell(LaneT& ln, const Tables& tb, const Consts& k, Fetch fetch_finalize_data) {
+    HostIO io;
+    std::memset(&io, 0xff, sizeof io);
+    while (ln.active()) {
+        ln.save(io);
+        LaneT ev;
+        std::memset((void*)&ev, 0xff, sizeof ev);
+        ev.load_request(io);
+        const bool was_eos = (ev.pc == PC_FINAL_EOS);
+        const double fv = ev.eval_request(tb, k);
+        ev.save_result(io, fv, was_eos);
+        LaneT bk;
+        std::memset((void*)&bk, 0xff, sizeof bk);
+        bk.arr = ln.arr;
+        double f;
+        bk.load(io, k, f);
+        if (bk.pc == PC_FINAL_EOS) fetch_finalize_data(bk);
+        bk.resume(k, f, 0u);
+        if (bk.fin_pending) { fetch_finalize_data(bk); bk.begin_finalize(k); }
+        ln = bk;
+    }
+}
 void put_stats(HcCellStat* cs, long idx, int nst, int netf, int nfe, int nni, int nnf, int nsetups, int nfe_ls, int flag) {
     if (!cs) return;
     cs[idx] = HcCellStat{nst, netf, nfe, nni, nnf, nsetups, nfe_ls, flag};
@@ -52,7 +85,7 @@ int hh_integrate_vec(const double* rates, const HcParams* prm, const HcFab* stat
         ln.jh = 1.0;
         ln.lastT = D(i, j, kk, 0); ln.lastNe = D(i, j, kk, 1);
         ln.start(k);
-        while (ln.active()) { const double f = ln.eval_request(tb, k); ln.resume(k, f, 0u); }
+        run_cell(ln, tb, k, [](Lane<PATH_VEC, ArrHost>&) {});
         D(i, j, kk, 0) = ln.outT; D(i, j, kk, 1) = ln.outNe;
         S(i, j, kk, 5) += S(i, j, kk, 0) * (ln.e_final - ln.e0);
         S(i, j, kk, 4) += S(i, j, kk, 0) * (ln.e_final - ln.e0);
@@ -88,7 +121,9 @@ int hh_integrate_struct(const double* rates, const HcParams* prm, const HcFab* s
         if (k.inhomo) { ln.zhi = D(i, j, kk, 2); ln.jh = (k.z > ln.zhi) ? 0.0 : 1.0; }
         ln.rho_out = N(i, j, kk, 0); ln.rhoe_new = N(i, j, kk, 5);
         ln.start(k);
-        while (ln.active()) { const double f = ln.eval_request(tb, k); ln.resume(k, f, 0u); }
+        // the cell data only the finalize step reads is not kept in the lane: fetched again when needed (as the kernel does)
+        const double c_rhoe_src = ln.rhoe_src, c_reset_src = ln.reset_src, c_rho_out = ln.rho_out, c_rhoe_new = ln.rhoe_new;
+        run_cell(ln, tb, k, [&](Lane<PATH_STRUCT, ArrHost>& l) { l.rhoe_src = c_rhoe_src; l.reset_src = c_reset_src; l.rho_out = c_rho_out; l.rhoe_new = c_rhoe_new; });
         D(i, j, kk, 0) = ln.outT; D(i, j, kk, 1) = ln.outNe;
         if (k.sdc_has_src) {
             I(i, j, kk, 0) = ln.IR;
