@@ -49,17 +49,22 @@ __device__ __forceinline__ int key_class(int key) {
 #endif
 }
 
+// Both accessors index the extern __shared__ array ITSELF with an integer lane number: through pointers kept in a struct the compiler
+// lost the address space and emitted generic loads / stores for the lane state (long-scoreboard stalls all over the bookkeeping phase,
+// +25 % kernel time: profiles/r2a_*).
 template <int STRIDE>
 struct ArrSmemT {
-    double* p;   // this lane's slot 0
-    __device__ __forceinline__ double& at(int slot) const { return p[slot * STRIDE]; }
+    int my;   // this lane's index
+    __device__ __forceinline__ double& at(int slot) const { return reinterpret_cast<double*>(s_raw)[slot * STRIDE + my]; }
 };
-// slot access of one lane for Lane::save / load / load_request / save_result
-template <int STRIDE>
+// slot access of one lane for Lane::save / load / load_request / save_result; BYTES_D = size of the double slots (the words follow them)
+template <int STRIDE, int ND_SLOTS>
 struct SmemIO {
-    double* pd; unsigned* pw;
-    __device__ __forceinline__ double& d(int slot) const { return pd[slot * STRIDE]; }
-    __device__ __forceinline__ unsigned& w(int slot) const { return pw[slot * STRIDE]; }
+    int my;
+    __device__ __forceinline__ double& d(int slot) const { return reinterpret_cast<double*>(s_raw)[slot * STRIDE + my]; }
+    __device__ __forceinline__ unsigned& w(int slot) const {
+        return reinterpret_cast<unsigned*>(s_raw + (size_t)ND_SLOTS * STRIDE * sizeof(double))[slot * STRIDE + my];
+    }
 };
 
 template <int PATH, int LANES>
@@ -119,8 +124,9 @@ template <int PATH, int LANES>
 __global__ void __launch_bounds__(LANES, HC_SORTED_CTAS) hc_sorted_kernel(const __grid_constant__ KernelArgs a) {
     using L = Layout<PATH, LANES>;
     using LaneT = typename L::LaneT;
-    using IO = SmemIO<LANES>;
-    __shared__ unsigned long long s_stats[S_COUNT];
+    using IO = SmemIO<LANES, L::ND>;
+    __shared__ unsigned long long s_pair[P_COUNT];        // packed diagnostics of the CTA
+    __shared__ int s_chunk[L::WARPS][6];                  // per warp: the current work-queue chunk (tile, j, k, x, x_end) and "queue empty"
     double* sd = reinterpret_cast<double*>(s_raw);
     unsigned* si = reinterpret_cast<unsigned*>(s_raw + L::bytes_d);
     unsigned short* s_order = reinterpret_cast<unsigned short*>(s_raw + L::bytes_d + L::bytes_i);
@@ -132,15 +138,12 @@ __global__ void __launch_bounds__(LANES, HC_SORTED_CTAS) hc_sorted_kernel(const 
     const Tables tb{a.ionx, a.iony, a.cool, a.logtab};   // all three in global memory (L1/L2)
     const Consts& c = a.k;
 
-    if (tid < S_COUNT) s_stats[tid] = 0ull;
+    if (tid < P_COUNT) s_pair[tid] = 0ull;
+    if (lane_id < 6) s_chunk[warp][lane_id] = 0;
     si[LaneT::WS_W0 * LANES + tid] = PC_IDLE;
     si[LaneT::WS_W1 * LANES + tid] = 0u;
     Totals tot;
-#pragma unroll
-    for (int i = 0; i < 7; ++i) tot.w[i] = 0ull;
-    tot.max_nst = 0u;
-    int w_tile = 0, w_j = 0, w_k = 0, w_x = 0, w_xend = 0;   // the warp's current chunk (warp-uniform)
-    bool queue_empty = false;
+    tot.iters_attempts = 0ull; tot.n_eos = 0u; tot.s_pair = s_pair;
     __syncthreads();
 #if defined(HC_PHASE_TIMING)
     unsigned long long ph[48];
@@ -193,19 +196,16 @@ __global__ void __launch_bounds__(LANES, HC_SORTED_CTAS) hc_sorted_kernel(const 
         bool active_after;
         {
             const int my = s_order[tid];
-            const IO io{sd + my, si + my};
+            const IO io{my};
             LaneT ln;
-            ln.arr.p = sd + my;
+            ln.arr.my = my;
             const unsigned w0_in = io.w(LaneT::WS_W0);
             double f = 0.0;
             // the lane's cell, packed: tile (20 bits) | k (12 bits), i (16) | j (16), relative to the tile.  Decoded only where the FABs
             // are touched (finalize data, store of a finished cell): once per cell, not once per round
             unsigned cell0 = 0u, cell1 = 0u;
-            ln.pc = (int)(w0_in & 15u);
-            if (ln.pc != PC_IDLE) {
-                ln.load(io, c, f);
-                cell0 = io.w(LaneT::WS_CELL0); cell1 = io.w(LaneT::WS_CELL1);
-            }
+            ln.load(io, c, f);
+            cell0 = io.w(LaneT::WS_CELL0); cell1 = io.w(LaneT::WS_CELL1);
             HC_TICK(16);
 #if defined(HC_PHASE_TIMING)
             const long long t_b0 = clock64();
@@ -229,45 +229,56 @@ __global__ void __launch_bounds__(LANES, HC_SORTED_CTAS) hc_sorted_kernel(const 
                     if (PATH == PATH_STRUCT) load_finalize_cell(ln, a, cell0, cell1);
                     ln.begin_finalize(c);
                 }
-                tot.w[5] += (unsigned long long)(unsigned)ln.attempts << 32;
+                tot.iters_attempts += (unsigned long long)(unsigned)ln.attempts << 32;
                 if (!ln.active()) store_cell_packed(ln, a, cell0, cell1, tot);
             }
             __syncwarp();
             HC_TICK(17);
-            // ---- refill: idle lanes take the next cells of the warp's chunk (new chunks from the global queue)
-            if (!queue_empty) {
+            // ---- refill: idle lanes take the next cells of the warp's chunk (new chunks from the global queue).  The chunk cursor is
+            // warp-uniform state that is touched once per finished cell: it lives in shared memory, not in registers
+            if (!s_chunk[warp][5]) {
                 bool need = !ln.active();
                 unsigned m = __ballot_sync(0xffffffffu, need);
-                while (m) {
-                    if (w_x >= w_xend) {
-                        unsigned long long chunk = 0;
-                        if (lane_id == 0) chunk = atomicAdd(a.queue, 1ull);
-                        chunk = __shfl_sync(0xffffffffu, chunk, 0);
-                        if (chunk >= (unsigned long long)a.nchunks) { queue_empty = true; break; }
-                        w_tile = find_tile_by_chunk(a.tiles, a.ntiles, (long long)chunk);
-                        const TileDesc& t = a.tiles[w_tile];
-                        const unsigned local = (unsigned)((long long)chunk - t.chunk_begin);
-                        const unsigned row = local / (unsigned)t.cpr, piece = local - row * (unsigned)t.cpr;
-                        const unsigned kk = row / (unsigned)t.ny;
-                        w_k = t.lo[2] + (int)kk;
-                        w_j = t.lo[1] + (int)(row - kk * (unsigned)t.ny);
-                        w_x = t.lo[0] + (int)piece * t.chunk_len;
-                        w_xend = min(w_x + t.chunk_len, t.lo[0] + t.nx);
+                if (m) {
+                    int w_tile = s_chunk[warp][0], w_j = s_chunk[warp][1], w_k = s_chunk[warp][2], w_x = s_chunk[warp][3], w_xend = s_chunk[warp][4];
+                    bool queue_empty = false;
+                    while (m) {
+                        if (w_x >= w_xend) {
+                            unsigned long long chunk = 0;
+                            if (lane_id == 0) chunk = atomicAdd(a.queue, 1ull);
+                            chunk = __shfl_sync(0xffffffffu, chunk, 0);
+                            if (chunk >= (unsigned long long)a.nchunks) { queue_empty = true; break; }
+                            w_tile = find_tile_by_chunk(a.tiles, a.ntiles, (long long)chunk);
+                            const TileDesc& t = a.tiles[w_tile];
+                            const unsigned local = (unsigned)((long long)chunk - t.chunk_begin);
+                            const unsigned row = local / (unsigned)t.cpr, piece = local - row * (unsigned)t.cpr;
+                            const unsigned kk = row / (unsigned)t.ny;
+                            w_k = t.lo[2] + (int)kk;
+                            w_j = t.lo[1] + (int)(row - kk * (unsigned)t.ny);
+                            w_x = t.lo[0] + (int)piece * t.chunk_len;
+                            w_xend = min(w_x + t.chunk_len, t.lo[0] + t.nx);
+                        }
+                        const int avail = w_xend - w_x;
+                        const int rk = __popc(m & lt_mask);
+                        if (need && rk < avail) {
+                            const TileDesc& t = a.tiles[w_tile];
+                            const int c_i = w_x + rk;
+                            cell0 = ((unsigned)w_tile << 12) | (unsigned)(w_k - t.lo[2]);
+                            cell1 = ((unsigned)(c_i - t.lo[0]) << 16) | (unsigned)(w_j - t.lo[1]);
+                            load_cell(ln, a, t, c_i, w_j, w_k);
+                            tot.iters_attempts += (unsigned long long)(unsigned)ln.attempts << 32;
+                            if (ln.active()) { need = false; io.w(LaneT::WS_CELL0) = cell0; io.w(LaneT::WS_CELL1) = cell1; }
+                            else store_cell(ln, a, t, c_i, w_j, w_k, tot);
+                        }
+                        w_x += min(avail, __popc(m));
+                        m = __ballot_sync(0xffffffffu, need);
                     }
-                    const int avail = w_xend - w_x;
-                    const int rk = __popc(m & lt_mask);
-                    if (need && rk < avail) {
-                        const TileDesc& t = a.tiles[w_tile];
-                        const int c_i = w_x + rk;
-                        cell0 = ((unsigned)w_tile << 12) | (unsigned)(w_k - t.lo[2]);
-                        cell1 = ((unsigned)(c_i - t.lo[0]) << 16) | (unsigned)(w_j - t.lo[1]);
-                        load_cell(ln, a, t, c_i, w_j, w_k);
-                        tot.w[5] += (unsigned long long)(unsigned)ln.attempts << 32;
-                        if (ln.active()) { need = false; io.w(LaneT::WS_CELL0) = cell0; io.w(LaneT::WS_CELL1) = cell1; }
-                        else store_cell(ln, a, t, c_i, w_j, w_k, tot);
+                    __syncwarp();
+                    if (lane_id == 0) {
+                        s_chunk[warp][0] = w_tile; s_chunk[warp][1] = w_j; s_chunk[warp][2] = w_k; s_chunk[warp][3] = w_x; s_chunk[warp][4] = w_xend;
+                        if (queue_empty) s_chunk[warp][5] = 1;
                     }
-                    w_x += min(avail, __popc(m));
-                    m = __ballot_sync(0xffffffffu, need);
+                    __syncwarp();
                 }
             }
             HC_TICK(18);
@@ -293,17 +304,17 @@ __global__ void __launch_bounds__(LANES, HC_SORTED_CTAS) hc_sorted_kernel(const 
 
         // ================= phase R: thread t evaluates the request of lane t
         {
-            const IO io{sd + tid, si + tid};
+            const IO io{tid};
             LaneT ln;
-            ln.arr.p = sd + tid;
+            ln.arr.my = tid;
             ln.pc = (int)(io.w(LaneT::WS_W0) & 15u);
             if (ln.active()) {
                 ln.load_request(io);
                 const bool is_eos = (ln.pc == PC_FINAL_EOS);
                 const double f = ln.eval_request(tb, c);
                 ln.save_result(io, f, is_eos);
-                tot.w[5] += (unsigned long long)(unsigned)ln.ne_iters;
-                tot.w[6] += (unsigned long long)(unsigned)ln.n_eos;
+                tot.iters_attempts += (unsigned long long)(unsigned)ln.ne_iters;
+                tot.n_eos += (unsigned)ln.n_eos;
             }
 #if defined(HC_PHASE_TIMING)
             ph[6] += ln.active() ? 1 : 0;
@@ -323,7 +334,7 @@ __global__ void __launch_bounds__(LANES, HC_SORTED_CTAS) hc_sorted_kernel(const 
     }
 #endif
 
-    flush_totals(tot, s_stats, a.dstats);
+    flush_totals(tot, a.dstats);
 }
 
 }  // namespace sorted

@@ -147,10 +147,14 @@ __device__ __forceinline__ void stage_tables(const KernelArgs& a, double* s_ionx
     for (int i = threadIdx.x; i < TAB_ROWS + 1; i += blockDim.x) s_iony[i] = __ldg(a.iony + i);
 }
 
-// per-thread running totals of the diagnostics (two 32-bit counters per word), reduced once at the end of the kernel
+// Diagnostics.  Per CELL counters are added to the CTA's totals in shared memory when the cell is stored (packed two 32-bit counters per
+// 64-bit word: 5 shared-memory atomics per cell); only the two per-ROUND quantities ride in registers.  (Fifteen registers of per-thread
+// totals were live through both phases of the kernel, next to a lane state that already spills at 168 registers per thread.)
+enum PairSlot { P_CELLS_FAILED = 0, P_FLOOR_NST, P_NFE_NFELS, P_NETF_NNI, P_NCFN_NSETUPS, P_NEITERS_ATTEMPTS, P_EOS, P_MAXNST, P_COUNT };
 struct Totals {
-    unsigned long long w[7];
-    unsigned int max_nst;
+    unsigned long long iters_attempts;   // sum of iterate_ne Newton iterations | step attempts << 32
+    unsigned int n_eos;
+    unsigned long long* s_pair;          // the CTA's packed totals (shared memory, P_COUNT words)
 };
 
 // gather one cell into a lane (HOT LOOP A of the reference: integrate_state_vec_3d.cpp:227-233,
@@ -234,13 +238,13 @@ __device__ __forceinline__ void store_cell(const LaneT& ln, const KernelArgs& a,
         const long long id = t.offset + ((long long)(k - t.lo[2]) * t.ny + (j - t.lo[1])) * t.nx + (i - t.lo[0]);
         a.cell_stats[id] = HcCellStat{ln.nst, ln.netf, ln.nfe, ln.nni, ln.nnf, ln.nsetups, ln.nfe_ls, ln.flag};
     }
-    tot.w[0] += 1ull | ((unsigned long long)(ln.flag < 0) << 32);
-    tot.w[1] += (unsigned long long)(unsigned)ln.floor_hit | ((unsigned long long)(unsigned)ln.nst << 32);
-    tot.w[2] += (unsigned long long)(unsigned)ln.nfe | ((unsigned long long)(unsigned)ln.nfe_ls << 32);
-    tot.w[3] += (unsigned long long)(unsigned)ln.netf | ((unsigned long long)(unsigned)ln.nni << 32);
-    tot.w[4] += (unsigned long long)(unsigned)ln.nnf | ((unsigned long long)(unsigned)ln.nsetups << 32);
+    atomicAdd(&tot.s_pair[P_CELLS_FAILED], 1ull | ((unsigned long long)(ln.flag < 0) << 32));
+    atomicAdd(&tot.s_pair[P_FLOOR_NST], (unsigned long long)(unsigned)ln.floor_hit | ((unsigned long long)(unsigned)ln.nst << 32));
+    atomicAdd(&tot.s_pair[P_NFE_NFELS], (unsigned long long)(unsigned)ln.nfe | ((unsigned long long)(unsigned)ln.nfe_ls << 32));
+    atomicAdd(&tot.s_pair[P_NETF_NNI], (unsigned long long)(unsigned)ln.netf | ((unsigned long long)(unsigned)ln.nni << 32));
+    atomicAdd(&tot.s_pair[P_NCFN_NSETUPS], (unsigned long long)(unsigned)ln.nnf | ((unsigned long long)(unsigned)ln.nsetups << 32));
     // (ne_iters, attempts and n_eos go to the totals round by round: they are not part of the lane state)
-    tot.max_nst = max(tot.max_nst, (unsigned)ln.nst);
+    atomicMax(&tot.s_pair[P_MAXNST], (unsigned long long)(unsigned)ln.nst);
 }
 
 template <class LaneT>
@@ -250,22 +254,21 @@ __device__ __forceinline__ void store_cell_packed(const LaneT& ln, const KernelA
     store_cell(ln, a, a.tiles[tile], i, j, k, tot);
 }
 
-__device__ __noinline__ void flush_totals(const Totals& tot, unsigned long long* s_stats, unsigned long long* dstats) {
-    // once per thread at the end of the kernel: shared-memory atomics, then one global atomic per counter per CTA
+__device__ __noinline__ void flush_totals(const Totals& tot, unsigned long long* dstats) {
+    // once per thread at the end of the kernel: the per-round counters join the CTA's packed totals, then one global atomic per counter per CTA
+    // (per-CTA 32-bit halves: 134 M cells over 148 CTAs x ~35 Newton iterations per cell = 3e7)
+    if (tot.iters_attempts) atomicAdd(&tot.s_pair[P_NEITERS_ATTEMPTS], tot.iters_attempts);
+    if (tot.n_eos) atomicAdd(&tot.s_pair[P_EOS], (unsigned long long)tot.n_eos);
+    __syncthreads();
     const int lo_slot[7] = {S_CELLS, S_FLOOR, S_NFE, S_NETF, S_NCFN, S_NEITERS, S_EOS};
     const int hi_slot[7] = {S_FAILED, S_NST, S_NFELS, S_NNI, S_NSETUPS, S_ATTEMPTS, -1};
-#pragma unroll 1
-    for (int i = 0; i < 7; ++i) {
-        const unsigned long long lo = tot.w[i] & 0xffffffffull, hi = tot.w[i] >> 32;
-        if (lo) atomicAdd(&s_stats[lo_slot[i]], lo);
-        if (hi && hi_slot[i] >= 0) atomicAdd(&s_stats[hi_slot[i]], hi);
+    if (threadIdx.x < 7) {
+        const unsigned long long v = tot.s_pair[threadIdx.x];
+        const unsigned long long lo = v & 0xffffffffull, hi = v >> 32;
+        if (lo) atomicAdd(&dstats[lo_slot[threadIdx.x]], lo);
+        if (hi && hi_slot[threadIdx.x] >= 0) atomicAdd(&dstats[hi_slot[threadIdx.x]], hi);
     }
-    atomicMax(&s_stats[S_MAXNST], (unsigned long long)tot.max_nst);
-    __syncthreads();
-    if (threadIdx.x < S_COUNT) {
-        if (threadIdx.x == S_MAXNST) atomicMax(&dstats[threadIdx.x], s_stats[threadIdx.x]);
-        else atomicAdd(&dstats[threadIdx.x], s_stats[threadIdx.x]);
-    }
+    if (threadIdx.x == 7) atomicMax(&dstats[S_MAXNST], tot.s_pair[P_MAXNST]);
 }
 
 // EOS kernel: one thread per cell, grid-stride over the cells of all tiles; ionization tables staged in shared memory.
