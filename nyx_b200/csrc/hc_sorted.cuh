@@ -153,64 +153,35 @@ __global__ void __launch_bounds__(LANES, HC_SORTED_CTAS) hc_sorted_kernel(const 
     const long long t_begin = t_last;
 #endif
 
-    for (;;) {
-        // ================= phase S: stable counting sort of the lanes by integrator phase
-        {
-            const int key = sort_key<LaneT>(si[LaneT::WS_W0 * LANES + tid], si[LaneT::WS_W1 * LANES + tid]);
-            const unsigned same = __match_any_sync(0xffffffffu, key);
-            const int rank = __popc(same & lt_mask);
-            if (lane_id < NKEY) s_cnt[lane_id * L::WARPS + warp] = 0;
-            __syncwarp();
-            if (rank == 0) s_cnt[key * L::WARPS + warp] = __popc(same);
-            HC_TICK(20);
-            __syncthreads();
-            HC_TICK(21);
-            // every warp computes its own bases: lane kk sums the counts of key kk over the warps (and over the warps before this one)
-            int tot_k = 0, pre_k = 0;
-            if (lane_id < NKEY) {
-#pragma unroll
-                for (int w = 0; w < L::WARPS; ++w) {
-                    const int cw = s_cnt[lane_id * L::WARPS + w];
-                    tot_k += cw;
-                    if (w < (int)warp) pre_k += cw;
-                }
-            }
-            int incl = tot_k;
-#pragma unroll
-            for (int o = 1; o < NKEY; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane_id >= o) incl += t; }
-            const int base_k = incl - tot_k + pre_k;   // first position of this warp's lanes with key == lane_id
-            s_order[__shfl_sync(0xffffffffu, base_k, key) + rank] = (unsigned short)tid;
-            HC_TICK(22);
-            __syncthreads();
-#if defined(HC_PHASE_TIMING)
-            if (rank == 0) {
-#pragma unroll
-                for (int kk = 0; kk < 8; ++kk) if (key_class(key) == kk) ph[8 + kk] += __popc(same);
-            }
-            ph[0] += 1;
+    // Round structure (two CTA barriers per SORTED round, none otherwise):
+    //   B   thread t runs the bookkeeping of lane `my` (stores a finished cell, refills an idle lane);
+    //   S   (every HC_SORT_EVERY-th round) counting sort by the keys the threads hold in registers: counts, barrier (which also decides
+    //       termination), bases + order, barrier; thread t adopts lane order[t];
+    //   R   thread t evaluates the request of ITS lane -- the lane whose bookkeeping it runs next, so no barrier separates R from B.
+    // In an unsorted round a warp keeps its lanes: a warp sorted into the long step-completing class has the short "request the Jacobian
+    // setup" class next, so over a pair of rounds the warps carry about the same bookkeeping load and meet at the barrier together.
+#if !defined(HC_SORT_EVERY)
+#define HC_SORT_EVERY 1
 #endif
-            HC_TICK(1);
-        }
-
-        // ================= phase B: bookkeeping of lane order[tid]
+    int my = tid;
+    for (unsigned round = 0;; ++round) {
+        // ================= phase B: bookkeeping of lane `my`
         bool active_after;
+        int key;
         {
-            const int my = s_order[tid];
             const IO io{my};
             LaneT ln;
             ln.arr.my = my;
-            const unsigned w0_in = io.w(LaneT::WS_W0);
             double f = 0.0;
             // the lane's cell, packed: tile (20 bits) | k (12 bits), i (16) | j (16), relative to the tile.  Decoded only where the FABs
             // are touched (finalize data, store of a finished cell): once per cell, not once per round
             unsigned cell0 = 0u, cell1 = 0u;
-            ln.load(io, c, f);
+            ln.load(io, c, f);   // unconditional, idle lanes included: a conditional load turns every lane field into a phi and the kernel spills
             cell0 = io.w(LaneT::WS_CELL0); cell1 = io.w(LaneT::WS_CELL1);
             HC_TICK(16);
 #if defined(HC_PHASE_TIMING)
             const long long t_b0 = clock64();
-            const unsigned w1_in = io.w(LaneT::WS_W1);
-            const int key0 = key_class(__shfl_sync(0xffffffffu, sort_key<LaneT>(w0_in, w1_in), 0));
+            const int key0 = key_class(__shfl_sync(0xffffffffu, sort_key<LaneT>(io.w(LaneT::WS_W0), io.w(LaneT::WS_W1)), 0));
 #endif
             const bool act0 = ln.active();
             const unsigned rmask = __ballot_sync(0xffffffffu, act0);
@@ -218,7 +189,7 @@ __global__ void __launch_bounds__(LANES, HC_SORTED_CTAS) hc_sorted_kernel(const 
 #if !defined(HC_DBG_CLASS)
 #define HC_DBG_CLASS 2   // 0: Newton-residual lanes, 2: Jacobian-setup lanes
 #endif
-            ln.dbg_on = (key0 == HC_DBG_CLASS) && (key_class(__shfl_sync(0xffffffffu, sort_key<LaneT>(w0_in, w1_in), 31)) == HC_DBG_CLASS);   // stage timing: warps made of one phase only
+            ln.dbg_on = (key0 == HC_DBG_CLASS) && (key_class(__shfl_sync(0xffffffffu, sort_key<LaneT>(io.w(LaneT::WS_W0), io.w(LaneT::WS_W1)), 31)) == HC_DBG_CLASS);   // stage timing: warps made of one phase only
             ln.dbg_last = clock64();
 #endif
             if (act0) {
@@ -288,6 +259,7 @@ __global__ void __launch_bounds__(LANES, HC_SORTED_CTAS) hc_sorted_kernel(const 
             else {
                 io.w(LaneT::WS_W0) = PC_IDLE; io.w(LaneT::WS_W1) = 0u;
             }
+            key = sort_key<LaneT>(io.w(LaneT::WS_W0), io.w(LaneT::WS_W1));
 #if defined(HC_PHASE_TIMING)
             {
                 const long long t_b1 = clock64();
@@ -298,15 +270,53 @@ __global__ void __launch_bounds__(LANES, HC_SORTED_CTAS) hc_sorted_kernel(const 
 #endif
         }
         HC_TICK(19);
-        const bool any_active = __syncthreads_or(active_after);
-        HC_TICK(3);
-        if (!any_active) break;   // nothing in flight and the queue is empty (also publishes the lanes for phase R)
 
-        // ================= phase R: thread t evaluates the request of lane t
+        // ================= phase S: stable counting sort of the lanes by integrator phase
+        if (HC_SORT_EVERY == 1 || (round % HC_SORT_EVERY) == 0) {
+            const unsigned same = __match_any_sync(0xffffffffu, key);
+            const int rank = __popc(same & lt_mask);
+            if (lane_id < NKEY) s_cnt[lane_id * L::WARPS + warp] = 0;
+            __syncwarp();
+            if (rank == 0) s_cnt[key * L::WARPS + warp] = __popc(same);
+            HC_TICK(20);
+            const bool any_active = __syncthreads_or(active_after);
+            HC_TICK(3);
+            if (!any_active) break;   // nothing in flight and the queue is empty
+            // every warp computes its own bases: lane kk sums the counts of key kk over the warps (and over the warps before this one)
+            int tot_k = 0, pre_k = 0;
+            if (lane_id < NKEY) {
+#pragma unroll
+                for (int w = 0; w < L::WARPS; ++w) {
+                    const int cw = s_cnt[lane_id * L::WARPS + w];
+                    tot_k += cw;
+                    if (w < (int)warp) pre_k += cw;
+                }
+            }
+            int incl = tot_k;
+#pragma unroll
+            for (int o = 1; o < NKEY; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane_id >= o) incl += t; }
+            const int base_k = incl - tot_k + pre_k;   // first position of this warp's lanes with key == lane_id
+            s_order[__shfl_sync(0xffffffffu, base_k, key) + rank] = (unsigned short)my;
+            HC_TICK(22);
+            __syncthreads();
+            my = s_order[tid];
+#if defined(HC_PHASE_TIMING)
+            if (rank == 0) {
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk) if (key_class(key) == kk) ph[8 + kk] += __popc(same);
+            }
+#endif
+            HC_TICK(1);
+        }
+#if defined(HC_PHASE_TIMING)
+        ph[0] += 1;
+#endif
+
+        // ================= phase R: thread t evaluates the request of its lane
         {
-            const IO io{tid};
+            const IO io{my};
             LaneT ln;
-            ln.arr.my = tid;
+            ln.arr.my = my;
             ln.pc = (int)(io.w(LaneT::WS_W0) & 15u);
             if (ln.active()) {
                 ln.load_request(io);
@@ -321,8 +331,6 @@ __global__ void __launch_bounds__(LANES, HC_SORTED_CTAS) hc_sorted_kernel(const 
 #endif
         }
         HC_TICK(4);
-        __syncthreads();
-        HC_TICK(5);
     }
 #if defined(HC_PHASE_TIMING)
     ph[7] = (unsigned long long)(clock64() - t_begin);

@@ -16,6 +16,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdarg>
 #include <cstdint>
 #include <cfloat>
@@ -23,6 +24,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <memory>
 #include <mutex>
 #include <vector>
 
@@ -443,10 +445,16 @@ struct DeviceTables {
     double* cool = nullptr;
     double* logtab = nullptr;
     int sm_count = 0;
-    bool attr_set[3] = {false, false, false};
+    std::atomic<bool> attr_set[3] = {{false}, {false}, {false}};   // set-once flags (the attribute calls themselves are idempotent)
 };
 std::mutex g_mu;
-std::vector<double> g_rates;          // host copy of the rates image
+// host copy of the rates image: replaced as a whole by hc_tables_upload under g_mu; every reader takes a reference-counted snapshot under the
+// same mutex, so a concurrent upload (another device, another thread) cannot pull the image from under a launch that is building its constants
+std::shared_ptr<const std::vector<double>> g_rates_ptr;
+std::shared_ptr<const std::vector<double>> rates_snapshot() {
+    std::lock_guard<std::mutex> lock(g_mu);
+    return g_rates_ptr;
+}
 DeviceTables g_dev[64];               // indexed by CUDA device ordinal
 
 int current_device(int& dev) {
@@ -526,9 +534,10 @@ int stream_grid(long long ncells, long long per_cta, int sms, int dflt_per_sm = 
 
 // multiprocessor count, queried once per device (the rank-2/4 streaming launchers do not need the rate tables of DeviceTables)
 int sm_count_of(int dev, int& sms) {
-    static int cached[64] = {0};
-    if (!cached[dev]) CUDA_TRY(cudaDeviceGetAttribute(&cached[dev], cudaDevAttrMultiProcessorCount, dev));
-    sms = cached[dev];
+    static std::atomic<int> cached[64];
+    int v = cached[dev].load(std::memory_order_relaxed);
+    if (!v) { CUDA_TRY(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev)); cached[dev].store(v, std::memory_order_relaxed); }
+    sms = v;
     return HC_OK;
 }
 
@@ -1001,7 +1010,7 @@ int hc_tables_upload(const double* rates, size_t n_doubles) {
     if (!rates || n_doubles != (size_t)HC_RATES_DOUBLES) { set_err("rates image must hold %d doubles", HC_RATES_DOUBLES); return HC_ERR_ARG; }
     int dev; if (int rc = current_device(dev)) return rc;
     std::lock_guard<std::mutex> lock(g_mu);
-    g_rates.assign(rates, rates + n_doubles);
+    g_rates_ptr = std::make_shared<const std::vector<double>>(rates, rates + n_doubles);
     std::vector<double> ionx, iony, cool, logtab;
     interleave_tables(rates, ionx, iony, cool);
     build_log10_table(logtab);
@@ -1021,8 +1030,9 @@ int hc_tables_upload(const double* rates, size_t n_doubles) {
 }
 
 int hc_uvb_at_z(double z, double* out6) {
-    if (g_rates.empty()) { set_err("hc_tables_upload has not been called"); return HC_ERR_NO_TABLES; }
-    const Uvb u = uvb_at_z(g_rates.data(), z);
+    const auto rates_sp = rates_snapshot();
+    if (!rates_sp) { set_err("hc_tables_upload has not been called"); return HC_ERR_NO_TABLES; }
+    const Uvb u = uvb_at_z(rates_sp->data(), z);
     out6[0] = u.ggh0; out6[1] = u.gghe0; out6[2] = u.gghep; out6[3] = u.eh0; out6[4] = u.ehe0; out6[5] = u.ehep;
     return HC_OK;
 }
@@ -1030,8 +1040,9 @@ int hc_uvb_at_z(double z, double* out6) {
 int hc_integrate_vec_batch(int ntiles, const HcFab* state, const HcFab* diag, const HcBox* tiles, double a, double dt,
                            const HcParams* prm, HcStats* stats, HcCellStat* cell_stats, void* stream) {
     if (!valid_params(prm) || (ntiles > 0 && (!state || !diag || !tiles)) || !(a > 0.0)) { set_err("bad argument"); return HC_ERR_ARG; }
-    if (g_rates.empty()) { set_err("hc_tables_upload has not been called"); return HC_ERR_NO_TABLES; }
-    const Consts k = make_consts_vec(g_rates.data(), *prm, a, dt);
+    const auto rates_sp = rates_snapshot();
+    if (!rates_sp) { set_err("hc_tables_upload has not been called"); return HC_ERR_NO_TABLES; }
+    const Consts k = make_consts_vec(rates_sp->data(), *prm, a, dt);
     const HcFab* fabs[2] = {state, diag};
     return launch(PATH_VEC, ntiles, fabs, 2, tiles, k, stats, cell_stats, (cudaStream_t)stream);
 }
@@ -1047,8 +1058,9 @@ int hc_integrate_struct_batch(int ntiles, const HcFab* s_old, const HcFab* diag,
     if (!valid_params(prm) || (ntiles > 0 && (!s_old || !diag || !s_new || !hydro_src || !reset_src || !ir || !tiles)) || !(a > 0.0) || !(a_end > 0.0)) {
         set_err("bad argument"); return HC_ERR_ARG;
     }
-    if (g_rates.empty()) { set_err("hc_tables_upload has not been called"); return HC_ERR_NO_TABLES; }
-    const Consts k = make_consts_struct(g_rates.data(), *prm, a, a_end, dt, sdc_iter);
+    const auto rates_sp = rates_snapshot();
+    if (!rates_sp) { set_err("hc_tables_upload has not been called"); return HC_ERR_NO_TABLES; }
+    const Consts k = make_consts_struct(rates_sp->data(), *prm, a, a_end, dt, sdc_iter);
     const HcFab* fabs[6] = {s_old, diag, s_new, hydro_src, reset_src, ir};
     return launch(PATH_STRUCT, ntiles, fabs, 6, tiles, k, stats, cell_stats, (cudaStream_t)stream);
 }
@@ -1062,8 +1074,9 @@ int hc_integrate_struct(const HcFab* s_old, const HcFab* diag, const HcFab* s_ne
 
 int hc_eos_T_given_Re(const HcFab* state, const HcFab* diag, HcBox tile, double a, const HcParams* prm, HcStats* stats, void* stream) {
     if (!valid_params(prm) || !state || !diag || !(a > 0.0)) { set_err("bad argument"); return HC_ERR_ARG; }
-    if (g_rates.empty()) { set_err("hc_tables_upload has not been called"); return HC_ERR_NO_TABLES; }
-    const Consts k = make_consts_eos(g_rates.data(), *prm, a);
+    const auto rates_sp = rates_snapshot();
+    if (!rates_sp) { set_err("hc_tables_upload has not been called"); return HC_ERR_NO_TABLES; }
+    const Consts k = make_consts_eos(rates_sp->data(), *prm, a);
     const HcFab* fabs[2] = {state, diag};
     return launch(PATH_EOS, 1, fabs, 2, &tile, k, stats, nullptr, (cudaStream_t)stream);
 }
@@ -1078,8 +1091,9 @@ int launch_eos(int path, int ntiles, const HcFab* const* fabs, int nf, const HcB
 int hc_compute_new_temp_batch(int ntiles, const HcFab* state, const HcFab* diag, const HcBox* tiles, double a, const HcParams* prm,
                               double small_temp, double large_temp, int max_temp_dt, HcStats* stats, void* stream) {
     if (!valid_params(prm) || ntiles < 0 || (ntiles > 0 && (!state || !diag || !tiles)) || !(a > 0.0)) { set_err("bad argument"); return HC_ERR_ARG; }
-    if (g_rates.empty()) { set_err("hc_tables_upload has not been called"); return HC_ERR_NO_TABLES; }
-    const Consts k = make_consts_eos(g_rates.data(), *prm, a);
+    const auto rates_sp = rates_snapshot();
+    if (!rates_sp) { set_err("hc_tables_upload has not been called"); return HC_ERR_NO_TABLES; }
+    const Consts k = make_consts_eos(rates_sp->data(), *prm, a);
     EosOpts eos; eos.mode = 1; eos.small_temp = small_temp; eos.large_temp = large_temp; eos.max_temp_dt = max_temp_dt;
     const HcFab* fabs[2] = {state, diag};
     return launch_eos(PATH_EOS, ntiles, fabs, 2, tiles, k, eos, stats, (cudaStream_t)stream);
@@ -1088,8 +1102,9 @@ int hc_compute_new_temp_batch(int ntiles, const HcFab* state, const HcFab* diag,
 int hc_reset_internal_energy_batch(int ntiles, const HcFab* state, const HcFab* diag, const HcFab* reset_src, const HcBox* tiles, double a,
                                    const HcParams* prm, double small_temp, int interp, void* stream) {
     if (!valid_params(prm) || ntiles < 0 || (ntiles > 0 && (!state || !diag || !reset_src || !tiles)) || !(a > 0.0)) { set_err("bad argument"); return HC_ERR_ARG; }
-    if (g_rates.empty()) { set_err("hc_tables_upload has not been called"); return HC_ERR_NO_TABLES; }
-    const Consts k = make_consts_eos(g_rates.data(), *prm, a);
+    const auto rates_sp = rates_snapshot();
+    if (!rates_sp) { set_err("hc_tables_upload has not been called"); return HC_ERR_NO_TABLES; }
+    const Consts k = make_consts_eos(rates_sp->data(), *prm, a);
     EosOpts eos; eos.small_temp = small_temp; eos.interp = interp;
     const HcFab* fabs[3] = {state, diag, reset_src};
     return launch_eos(PATH_RESET_E, ntiles, fabs, 3, tiles, k, eos, nullptr, (cudaStream_t)stream);
@@ -1098,9 +1113,10 @@ int hc_reset_internal_energy_batch(int ntiles, const HcFab* state, const HcFab* 
 int hc_integrate_vec_host(int ntiles, const HcFab* state, const HcFab* diag, const HcBox* tiles, double a, double dt,
                           const HcParams* prm, HcStats* stats) {
     if (ntiles <= 0 || !state || !diag || !tiles || !valid_params(prm) || !(a > 0.0)) { set_err("bad argument"); return HC_ERR_ARG; }
-    if (g_rates.empty()) { set_err("hc_tables_upload has not been called"); return HC_ERR_NO_TABLES; }
+    const auto rates_sp = rates_snapshot();
+    if (!rates_sp) { set_err("hc_tables_upload has not been called"); return HC_ERR_NO_TABLES; }
     if (stats) std::memset(stats, 0, sizeof *stats);
-    const Consts k = make_consts_vec(g_rates.data(), *prm, a, dt);
+    const Consts k = make_consts_vec(rates_sp->data(), *prm, a, dt);
     // diag(Temp, Ne) are dead inputs of the Strang path (eos_hc.H:151; load_cell never reads them): pure outputs, not uploaded
     std::vector<HostSlot> slots = {{state, {DENS, EDEN, EINT}, {EDEN, EINT}}, {diag, {}, {TEMP, NE}}};
     return run_host(PATH_VEC, ntiles, slots, tiles, k, stats);
@@ -1112,9 +1128,10 @@ int hc_integrate_struct_host(int ntiles, const HcFab* s_old, const HcFab* diag, 
     if (ntiles <= 0 || !s_old || !diag || !s_new || !hydro_src || !reset_src || !ir || !tiles || !valid_params(prm) || !(a > 0.0) || !(a_end > 0.0)) {
         set_err("bad argument"); return HC_ERR_ARG;
     }
-    if (g_rates.empty()) { set_err("hc_tables_upload has not been called"); return HC_ERR_NO_TABLES; }
+    const auto rates_sp = rates_snapshot();
+    if (!rates_sp) { set_err("hc_tables_upload has not been called"); return HC_ERR_NO_TABLES; }
     if (stats) std::memset(stats, 0, sizeof *stats);
-    const Consts k = make_consts_struct(g_rates.data(), *prm, a, a_end, dt, sdc_iter);
+    const Consts k = make_consts_struct(rates_sp->data(), *prm, a, a_end, dt, sdc_iter);
     const bool src = (sdc_iter >= 0);   // with sdc_iter < 0 the update goes to S_old (f_rhs_struct.H:430-444 mirrored in store_cell)
     std::vector<HostSlot> slots = {
         {s_old, {DENS, EDEN, EINT}, src ? std::vector<int>{} : std::vector<int>{EDEN, EINT}},
@@ -1129,9 +1146,10 @@ int hc_integrate_struct_host(int ntiles, const HcFab* s_old, const HcFab* diag, 
 int hc_compute_new_temp_host(int ntiles, const HcFab* state, const HcFab* diag, const HcBox* tiles, double a, const HcParams* prm,
                              double small_temp, double large_temp, int max_temp_dt, HcStats* stats) {
     if (ntiles <= 0 || !state || !diag || !tiles || !valid_params(prm) || !(a > 0.0)) { set_err("bad argument"); return HC_ERR_ARG; }
-    if (g_rates.empty()) { set_err("hc_tables_upload has not been called"); return HC_ERR_NO_TABLES; }
+    const auto rates_sp = rates_snapshot();
+    if (!rates_sp) { set_err("hc_tables_upload has not been called"); return HC_ERR_NO_TABLES; }
     if (stats) std::memset(stats, 0, sizeof *stats);
-    const Consts k = make_consts_eos(g_rates.data(), *prm, a);
+    const Consts k = make_consts_eos(rates_sp->data(), *prm, a);
     EosOpts eos; eos.mode = 1; eos.small_temp = small_temp; eos.large_temp = large_temp; eos.max_temp_dt = max_temp_dt;
     std::vector<HostSlot> slots = {{state, {0, 1, 2, 3, EDEN, EINT}, {EDEN, EINT}}, {diag, {TEMP, NE}, {TEMP, NE}}};
     return run_host(PATH_EOS, ntiles, slots, tiles, k, stats, &eos);
@@ -1140,8 +1158,9 @@ int hc_compute_new_temp_host(int ntiles, const HcFab* state, const HcFab* diag, 
 int hc_reset_internal_energy_host(int ntiles, const HcFab* state, const HcFab* diag, const HcFab* reset_src, const HcBox* tiles, double a,
                                   const HcParams* prm, double small_temp, int interp) {
     if (ntiles <= 0 || !state || !diag || !reset_src || !tiles || !valid_params(prm) || !(a > 0.0)) { set_err("bad argument"); return HC_ERR_ARG; }
-    if (g_rates.empty()) { set_err("hc_tables_upload has not been called"); return HC_ERR_NO_TABLES; }
-    const Consts k = make_consts_eos(g_rates.data(), *prm, a);
+    const auto rates_sp = rates_snapshot();
+    if (!rates_sp) { set_err("hc_tables_upload has not been called"); return HC_ERR_NO_TABLES; }
+    const Consts k = make_consts_eos(rates_sp->data(), *prm, a);
     EosOpts eos; eos.small_temp = small_temp; eos.interp = interp;
     std::vector<HostSlot> slots = {{state, {0, 1, 2, 3, EDEN, EINT}, {EDEN, EINT}}, {diag, {NE}, {}}, {reset_src, {0}, {0}}};
     return run_host(PATH_RESET_E, ntiles, slots, tiles, k, nullptr, &eos);

@@ -30,6 +30,7 @@
 #endif
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <string>
@@ -92,6 +93,17 @@ HcParams make_params(const NyxFlags& fl, long int old_max_steps) {
 // for the rows next to the path (EOS only: no integrator flags needed)
 HcParams eos_params() { return make_params(NyxFlags{1e-4, 1e-4, 0, 0}, 3); }
 
+// GPU build of AMReX: launch on AMReX's current stream, so that the kernels are ordered with the host application's own (no device-wide
+// synchronisation); the statistics read-back -- a stream synchronisation -- only where somebody uses it (nyx.use_typical_steps, or
+// NYX_HC_STATS=1 for nyx_hc_last_stats())
+#ifdef AMREX_USE_GPU
+void* nyx_stream() { return (void*)amrex::Gpu::gpuStream(); }
+bool want_stats(const NyxFlags& fl) {
+    static const bool env = std::getenv("NYX_HC_STATS") != nullptr;
+    return env || fl.use_typical_steps != 0;
+}
+#endif
+
 int check(int rc) {
     if (rc != HC_OK) amrex::Abort(std::string("nyx_hc: ") + hc_last_error());
     return 0;   // like the reference: per-cell integrator failures are not errors (they are counted in HcStats)
@@ -129,7 +141,7 @@ int vec_batch(std::vector<HcFab>& s, std::vector<HcFab>& d, std::vector<HcBox>& 
     const HcParams p = make_params(fl, old_max);
     HcStats st{};
 #ifdef AMREX_USE_GPU
-    const int rc = hc_integrate_vec_batch((int)t.size(), s.data(), d.data(), t.data(), a, dt, &p, &st, nullptr, nullptr);
+    const int rc = hc_integrate_vec_batch((int)t.size(), s.data(), d.data(), t.data(), a, dt, &p, want_stats(fl) ? &st : nullptr, nullptr, nyx_stream());
 #else
     const int rc = hc_integrate_vec_host((int)t.size(), s.data(), d.data(), t.data(), a, dt, &p, &st);
 #endif
@@ -194,7 +206,7 @@ int struct_batch(std::vector<HcFab> f[6], std::vector<HcBox>& t, Real a, Real a_
     HcStats st{};
 #ifdef AMREX_USE_GPU
     const int rc = hc_integrate_struct_batch((int)t.size(), f[0].data(), f[1].data(), f[2].data(), f[3].data(), f[4].data(), f[5].data(),
-                                             t.data(), a, a_end, dt, sdc_iter, &p, &st, nullptr, nullptr);
+                                             t.data(), a, a_end, dt, sdc_iter, &p, want_stats(fl) ? &st : nullptr, nullptr, nyx_stream());
 #else
     const int rc = hc_integrate_struct_host((int)t.size(), f[0].data(), f[1].data(), f[2].data(), f[3].data(), f[4].data(), f[5].data(),
                                             t.data(), a, a_end, dt, sdc_iter, &p, &st);
@@ -336,7 +348,7 @@ void nyx_hc_compute_new_temp(MultiFab& S_new, MultiFab& D_new, Real a, Real smal
     const HcParams p = eos_params();
     HcStats st{};
 #ifdef AMREX_USE_GPU
-    check(hc_compute_new_temp_batch((int)t.size(), s.data(), d.data(), t.data(), a, &p, small_temp, large_temp, max_temp_dt, &st, nullptr));
+    check(hc_compute_new_temp_batch((int)t.size(), s.data(), d.data(), t.data(), a, &p, small_temp, large_temp, max_temp_dt, nullptr, nyx_stream()));
 #else
     check(hc_compute_new_temp_host((int)t.size(), s.data(), d.data(), t.data(), a, &p, small_temp, large_temp, max_temp_dt, &st));
 #endif
@@ -354,7 +366,7 @@ void nyx_hc_reset_internal_energy(MultiFab& S_new, MultiFab& D_new, MultiFab& re
     ensure_tables();
     const HcParams p = eos_params();
 #ifdef AMREX_USE_GPU
-    check(hc_reset_internal_energy_batch((int)t.size(), s.data(), d.data(), r.data(), t.data(), a, &p, small_temp, interp, nullptr));
+    check(hc_reset_internal_energy_batch((int)t.size(), s.data(), d.data(), r.data(), t.data(), a, &p, small_temp, interp, nyx_stream()));
 #else
     check(hc_reset_internal_energy_host((int)t.size(), s.data(), d.data(), r.data(), t.data(), a, &p, small_temp, interp));
 #endif
@@ -408,8 +420,7 @@ void nyx_hc_init_zhi(MultiFab& D_new, MultiFab& zhi, int ratio)
     }
     if (t.empty()) return;
 #ifdef AMREX_USE_GPU
-    check(hc_init_zhi_batch((int)t.size(), d.data(), z.data(), ratio, t.data(), nullptr));
-    check(hc_sync(nullptr));
+    check(hc_init_zhi_batch((int)t.size(), d.data(), z.data(), ratio, t.data(), nyx_stream()));
 #else
     // CPU build of AMReX: the same kernel through the host-buffer staging path (no CPU loop on the product path)
     check(hc_init_zhi_host((int)t.size(), d.data(), z.data(), ratio, t.data()));

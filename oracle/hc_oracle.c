@@ -1,3 +1,9 @@
+/*
+ * Licence note: the BDF / Newton / diagonal-solver logic below follows SUNDIALS CVODE 6.3.0 (BSD 3-Clause, Copyright (c) 2002-2022 Lawrence
+ * Livermore National Security and Southern Methodist University) and the right-hand side / EOS follow Nyx (BSD-style, Copyright (c) 2017 The
+ * Regents of the University of California, through Lawrence Berkeley National Laboratory) statement by statement where identical results
+ * require it; both notices are reproduced in THIRD_PARTY_NOTICES.md.
+ */
 /* TEST INFRASTRUCTURE ONLY -- see hc_oracle.h.  Plain C11, compiled with -ffp-contract=off so that
  * every product and sum is rounded separately, as in the reference's x86-64 GCC -O3 build.
  *
