@@ -163,6 +163,9 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
+_HOST_THREADS = None
+
+
 def cpu_reference_run(args, path, boxes_idx, boxes, budget_s, min_boxes=1, calibrated=None):
     """Times the reference's own CPU implementation (oracle/_ref OpenMP build; C port if it is absent) on as many
     boxes of the workload as fit `budget_s` (at least `min_boxes`).  Returns (cells_per_s, info dict)."""
@@ -171,10 +174,14 @@ def cpu_reference_run(args, path, boxes_idx, boxes, budget_s, min_boxes=1, calib
     a = 1.0 / (1.0 + args.z)
     dt = synth.step_dt(args.z)
     kind, cores, ref, port = "reference", 1, None, None
+    # all the host threads the box offers (torchrun exports OMP_NUM_THREADS=1 to its children; NYX_REF_THREADS overrides).  Counted BEFORE the
+    # library is loaded: with OMP_PROC_BIND set, libgomp pins the calling thread to one core as it initialises
+    global _HOST_THREADS
+    if _HOST_THREADS is None:
+        _HOST_THREADS = len(os.sched_getaffinity(0))
     try:
         ref = pyref.Reference("omp")
-        # all the host threads the box offers (torchrun exports OMP_NUM_THREADS=1 to its children; NYX_REF_THREADS overrides)
-        want = int(os.environ.get("NYX_REF_THREADS", "0")) or len(os.sched_getaffinity(0))
+        want = int(os.environ.get("NYX_REF_THREADS", "0")) or _HOST_THREADS
         ref.set("omp.num_threads", want)
         cores = ref.max_threads()
     except (FileNotFoundError, OSError):
@@ -229,6 +236,8 @@ def run_reference_arm(args):
         return
     # OMP_PROC_BIND=close, all host threads.  Must be in the environment before libgomp initialises (oracle/_ref is
     # loaded below); torchrun's OMP_NUM_THREADS=1 is overridden through omp_set_num_threads in cpu_reference_run.
+    global _HOST_THREADS
+    _HOST_THREADS = len(os.sched_getaffinity(0))
     os.environ["OMP_PROC_BIND"] = "close"
     os.environ.pop("OMP_NUM_THREADS", None)
     from nyx_b200 import sharded

@@ -214,6 +214,10 @@ int hc_measure_fp64_peak(double* flops_per_s);
  * by the same inline function the RHS fast path uses; bad[i] != 0 where the fast path would hand over to the library log10 */
 int hc_selftest_log10(const double* x, double* y, int* bad, long long n);
 
+/* self-test of the kernels' division by the table spacing (hc_device.cuh: div_delta_t, a three-instruction correctly rounded quotient by the
+ * compile-time constant (TCOOLMAX - TCOOLMIN) / NCOOLTAB): y[i] = x[i] / DELTA_T for n HOST doubles, evaluated on the device */
+int hc_selftest_div_delta_t(const double* x, double* y, long long n);
+
 /* blocks until work queued on `stream` is done (cudaStreamSynchronize) */
 int hc_sync(void* stream);
 

@@ -121,6 +121,7 @@ def declare(lib, prefix="hc_"):
     lib.hc_init_zhi_host.argtypes = [C.c_int, fp, fp, C.c_int, bp]
     lib.hc_measure_fp64_peak.argtypes = [_dp]
     lib.hc_selftest_log10.argtypes = [_dp, _dp, C.POINTER(C.c_int), C.c_longlong]
+    lib.hc_selftest_div_delta_t.argtypes = [_dp, _dp, C.c_longlong]
     lib.hc_sync.argtypes = [C.c_void_p]
     return lib
 
@@ -272,6 +273,13 @@ class NyxHC:
         bad = np.empty(x.size, dtype=np.int32)
         self.check(self.lib.hc_selftest_log10(x.ctypes.data_as(_dp), y.ctypes.data_as(_dp), bad.ctypes.data_as(C.POINTER(C.c_int)), x.size))
         return y, bad
+
+    def selftest_div_delta_t(self, x):
+        """x / DELTA_T through the kernels' constant-divisor fast path"""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.empty_like(x)
+        self.check(self.lib.hc_selftest_div_delta_t(x.ctypes.data_as(_dp), y.ctypes.data_as(_dp), x.size))
+        return y
 
     def sync(self, stream=None):
         self.check(self.lib.hc_sync(stream))

@@ -192,6 +192,15 @@ __global__ void __launch_bounds__(LANES, HC_SORTED_CTAS) hc_sorted_kernel(const 
             ln.dbg_on = (key0 == HC_DBG_CLASS) && (key_class(__shfl_sync(0xffffffffu, sort_key<LaneT>(io.w(LaneT::WS_W0), io.w(LaneT::WS_W1)), 31)) == HC_DBG_CLASS);   // stage timing: warps made of one phase only
             ln.dbg_last = clock64();
 #endif
+#if !defined(HC_FIN_PREFETCH)
+#define HC_FIN_PREFETCH 0   // measured (profiles/r2_s8_micro.log): prefetching the finalize / store lines of a last-step lane gains nothing (56.7 vs 57.4 ms Strang, 88.8 vs 90.9 ms SDC at 256^3)
+#endif
+            if (HC_FIN_PREFETCH && act0) {
+                // a step attempt that reaches tout ends the integration if it passes: get the lines the finalize step / the store will wait for
+                // on their way now (SDC path: finalize and store happen at the end of THIS chain; Strang path: the store follows one round later)
+                const bool last_step = (ln.pc == PC_NLS_RES || ln.pc == PC_LSETUP_F) && ((ln.tn - c.tout) * ln.h >= 0.0);
+                if (last_step) prefetch_finalize_cell<PATH>(a, cell0, cell1);
+            }
             if (act0) {
                 // (SDC path) the cell data only the finalize step reads is fetched again when a lane gets there: it is not part of the lane state
                 if (PATH == PATH_STRUCT && ln.pc == PC_FINAL_EOS) load_finalize_cell(ln, a, cell0, cell1);

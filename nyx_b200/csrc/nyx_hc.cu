@@ -216,6 +216,29 @@ __device__ __forceinline__ void load_finalize_cell(LaneT& ln, const KernelArgs& 
     ln.rhoe_new = t.f[F_SNEW].p[no + EINT * t.f[F_SNEW].nstride];
 }
 
+// The finalize step of a cell waits for DRAM twice if nothing is done about it: the finalize-only inputs (SDC path) and the read-modify-write
+// of (rho e, rho E) in store_cell.  A lane whose current step attempt reaches tout -- known before the bookkeeping chain starts -- therefore
+// prefetches those lines; by the time the chain gets to the finalize step they are in L1 / L2.
+__device__ __forceinline__ void prefetch_line(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+template <int PATH>
+__device__ __forceinline__ void prefetch_finalize_cell(const KernelArgs& a, unsigned cell0, unsigned cell1) {
+    int tile, i, j, k;
+    unpack_cell(a, cell0, cell1, tile, i, j, k);
+    const TileDesc& t = a.tiles[tile];
+    if (PATH == PATH_STRUCT && a.k.sdc_has_src) {
+        prefetch_line(t.f[F_HSRC].p + fab_off(t.f[F_HSRC], i, j, k) + EINT * t.f[F_HSRC].nstride);
+        prefetch_line(t.f[F_RSRC].p + fab_off(t.f[F_RSRC], i, j, k));
+        const double* pn = t.f[F_SNEW].p + fab_off(t.f[F_SNEW], i, j, k);
+        prefetch_line(pn + DENS * t.f[F_SNEW].nstride);
+        prefetch_line(pn + EINT * t.f[F_SNEW].nstride);
+        prefetch_line(pn + EDEN * t.f[F_SNEW].nstride);
+    } else {
+        const double* ps = t.f[F_STATE].p + fab_off(t.f[F_STATE], i, j, k);
+        prefetch_line(ps + EINT * t.f[F_STATE].nstride);
+        prefetch_line(ps + EDEN * t.f[F_STATE].nstride);
+    }
+}
+
 // scatter a finished cell (HOT LOOP C: integrate_state_vec_3d.cpp:317-321, f_rhs_struct.H:290-291,438-444)
 template <class LaneT>
 __device__ __forceinline__ void store_cell(const LaneT& ln, const KernelArgs& a, const TileDesc& t, int i, int j, int k, Totals& tot) {
@@ -430,6 +453,10 @@ __global__ void hc_log10_selftest_kernel(const double* logtab, const double* x, 
         y[i] = fast_log10(logtab, x[i], b);
         bad[i] = b ? 1 : 0;
     }
+}
+
+__global__ void hc_divdelta_selftest_kernel(const double* x, double* y, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) y[i] = div_delta_t(x[i]);
 }
 
 // ---------------------------------------------------------------------------------------------- host state
@@ -1355,6 +1382,21 @@ int hc_selftest_log10(const double* x, double* y, int* bad, long long n) {
     CUDA_TRY(cudaMemcpy(y, dy, n * sizeof(double), cudaMemcpyDeviceToHost));
     CUDA_TRY(cudaMemcpy(bad, db, n * sizeof(int), cudaMemcpyDeviceToHost));
     cudaFree(dx); cudaFree(dy); cudaFree(db);
+    return HC_OK;
+}
+
+int hc_selftest_div_delta_t(const double* x, double* y, long long n) {
+    if (!x || !y || n < 0) { set_err("bad argument"); return HC_ERR_ARG; }
+    int dev; if (int rc = current_device(dev)) return rc;
+    if (n == 0) return HC_OK;
+    double *dx = nullptr, *dy = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&dx, n * sizeof(double)));
+    CUDA_TRY(cudaMalloc((void**)&dy, n * sizeof(double)));
+    CUDA_TRY(cudaMemcpy(dx, x, n * sizeof(double), cudaMemcpyHostToDevice));
+    hc_divdelta_selftest_kernel<<<148, 256>>>(dx, dy, n);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpy(y, dy, n * sizeof(double), cudaMemcpyDeviceToHost));
+    cudaFree(dx); cudaFree(dy);
     return HC_OK;
 }
 

@@ -88,6 +88,23 @@ def test_fast_log10_on_device(hc_lib):
     assert bad.tolist() == [1, 1, 1, 1, 1, 1]
 
 
+def test_div_delta_t_on_device(hc_lib):
+    """the table-position quotient log10(T) / DELTA_T of the RHS fast path (three FP64 instructions, constant reciprocal + one FMA residual)
+    equals IEEE division bit for bit: random arguments over the table range, and every table node +- 3 ulp"""
+    rng = np.random.default_rng(5)
+    d = 9.0 / 2000
+    nodes = np.arange(1, 2001) * d
+    near = [nodes]
+    for k in range(3):
+        near += [np.nextafter(near[-1] if k else nodes, 10.0)]
+    lo = nodes
+    for k in range(3):
+        lo = np.nextafter(lo, -1.0); near.append(lo)
+    x = np.concatenate([rng.uniform(0.5 * d, 9.0, 2000000), rng.uniform(0.5 * d, 0.02, 100000)] + near)
+    y = hc_lib.selftest_div_delta_t(x)
+    assert np.array_equal(y, x / d)
+
+
 @pytest.mark.parametrize("z,n,seed", [(3.0, 32, 11), (2.0, 32, 12), (6.0, 32, 13), (3.0, 7, 14)])
 def test_vec_matches_oracle(hc_lib, port, z, n, seed):
     torch = _torch()
