@@ -24,9 +24,16 @@ namespace sorted {
 // 364 bytes per lane on the Strang path, 420 on the SDC path: 384 lanes fit the 164 KB shared-memory carve-out, which leaves the L1 92 KB
 // for the rate tables and the stack (round 1: 496 / 592 bytes, 196 / 228 KB carve-out, 60 / 28 KB of L1).
 #if !defined(HC_SORT_FINE)
-#define HC_SORT_FINE 2
+#define HC_SORT_FINE 2   // (3: additionally split by "this step attempt reaches tout": measured 56.26 vs 56.04 ms Strang, 88.07 vs 88.75 ms SDC at 256^3 -- no gain, profiles/r2_s10_sortkey_laststep.log)
 #endif
-#if HC_SORT_FINE
+#if HC_SORT_FINE == 3
+// (order q in {1, 2, 3+}) x (qwait == 1 or not: the step that prepares an order change) x (last step or not: a lane whose step attempt
+// reaches tout skips the whole set-up of the next step and runs the finalize step, the store of the cell and the refill of its lane
+// instead -- DRAM round trips and, on the SDC path, ~10 divisions) x (Newton-residual lane | Jacobian-setup lane, side by side)
+constexpr int NSUB = 6;
+enum Key { K_NEWTON = 0, K_SETUP_REQ = 4 * NSUB, K_HIN, K_INIT, K_ETEST, K_FINAL, K_IDLE, NKEY };
+constexpr int K_LSETUP = 1;
+#elif HC_SORT_FINE
 // the step-completing lanes are split further by (order q, qwait), which decide loop trip counts and branches of their chain
 // (measured in one gpurun call, best of 6, twice: 68.43 / 68.48 ms against 69.48 / 71.87 ms with the 8 plain keys; HC_SORT_FINE == 2
 // interleaves the two step-completing phases within each (q, qwait) class: 62.15 / 61.60 ms against 64.66 / 65.86 ms for == 1)
@@ -40,7 +47,7 @@ enum Key { K_NEWTON = 0, K_SETUP_REQ, K_LSETUP, K_HIN, K_INIT, K_ETEST, K_FINAL,
 static_assert(NKEY <= 32, "one lane per key in the base computation");
 // the 8 integrator phases behind the keys (diagnostics): NEWTON, SETUP_REQ, LSETUP, HIN, INIT, ETEST, FINAL, IDLE
 __device__ __forceinline__ int key_class(int key) {
-#if HC_SORT_FINE == 2
+#if HC_SORT_FINE >= 2
     return (key < K_SETUP_REQ) ? ((key & 1) ? 2 : 0) : (key == K_SETUP_REQ) ? 1 : 3 + (key - K_HIN);
 #elif HC_SORT_FINE
     return (key < K_LSETUP) ? 0 : (key < K_SETUP_REQ) ? 2 : (key == K_SETUP_REQ) ? 1 : 3 + (key - K_HIN);
@@ -85,14 +92,17 @@ template <class LaneT>
 __device__ __forceinline__ int sort_key(unsigned w0, unsigned w1) {
     const int pc = (int)(w0 & 15u);
     const bool callSetup = (w1 >> 8) & 1u, res_at_top = (w1 >> 9) & 1u;
-#if HC_SORT_FINE
+#if HC_SORT_FINE == 3
+    const int q = (int)((w0 >> 4) & 15u), qwait = (int)((w0 >> 12) & 15u);
+    const int sub = ((min(max(q, 1), 3) - 1) * 2 + (qwait == 1 ? 0 : 1)) * 2 + (int)((w1 >> 21) & 1u);
+#elif HC_SORT_FINE
     const int q = (int)((w0 >> 4) & 15u), qwait = (int)((w0 >> 12) & 15u);
     const int sub = (min(max(q, 1), 3) - 1) * 3 + (min(max(qwait, 1), 3) - 1);
 #else
     const int sub = 0;
 #endif
     switch (pc) {
-#if HC_SORT_FINE == 2
+#if HC_SORT_FINE >= 2
     // the two step-completing phases interleaved: key = 2 * (q, qwait class) + phase, so that a Newton-residual lane sits next to the
     // Jacobian-setup lanes of the same order -- they differ in their first two stages only and share the long tail of the chain
     case PC_NLS_RES: return (res_at_top && callSetup) ? K_SETUP_REQ : K_NEWTON + 2 * sub;
