@@ -372,6 +372,7 @@ class PathBench:
             sampler.start()
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         stats = None
+        drains = []
         wall0 = time.perf_counter()
         for s in range(steps):
             self.restore_device()      # untimed: every step integrates the same input (the path updates its FABs in place)
@@ -379,12 +380,14 @@ class PathBench:
             ev[s][0].record(self.stream)
             stats = self.step_device()   # one persistent kernel + the 112-byte statistics read-back
             ev[s][1].record(self.stream)
+            drains.append(ctx["hc"].last_launch_timing())
         ctx["barrier"]()
         wall = time.perf_counter() - wall0
         clocks = sampler.result() if sampler else None
         ms_steps = [e0.elapsed_time(e1) for e0, e1 in ev]
         t_local = sum(ms_steps) * 1e-3
-        return {"t_local": t_local, "t_max": ctx["allmax"](t_local), "ms_steps": ms_steps, "stats": stats, "clocks": clocks, "wall": wall}
+        return {"t_local": t_local, "t_max": ctx["allmax"](t_local), "ms_steps": ms_steps, "stats": stats, "clocks": clocks, "wall": wall,
+                "kernel_ms": float(np.mean([d[0] for d in drains])), "drain_ms": float(np.mean([d[1] for d in drains]))}
 
     def roofline(self, leg, steps):
         from nyx_b200 import sharded
@@ -525,6 +528,7 @@ def main():
             else:
                 e2e = pb.e2e_leg(args.steps, gstats["n_cells"])
         rec = {"value": value, "unit": UNIT, "ms_per_step": 1e3 * leg["t_max"] / steps_p, "steps": steps_p, "roofline": roof, "e2e": e2e,
+               "kernel_ms_this_rank": leg["kernel_ms"], "drain_tail_ms_this_rank": leg["drain_ms"],
                "stats": gstats, "ms_steps": leg["ms_steps"], "clocks": leg["clocks"], "workload": workload_name(args, path)}
         results[path] = rec
         if path == args.path:
@@ -552,6 +556,7 @@ def main():
             strong[path] = {"value": gs["n_cells"] * steps_s / leg["t_max"], "unit": UNIT, "ms_per_step": ms, "steps": steps_s,
                             "cells_total": gs["n_cells"], "boxes_per_gpu": len(smine), "ms_per_step_n1_rank0": float(t1.item()),
                             "efficiency_vs_n1": float(t1.item()) / (world * ms), "max_nst": gs["max_nst"],
+                            "kernel_ms_this_rank": leg["kernel_ms"], "drain_tail_ms_this_rank": leg["drain_ms"],
                             "ms_steps_this_rank": leg["ms_steps"]}
             pbs.free()
             del pbs
@@ -573,7 +578,7 @@ def main():
                     "numa": numa}),
                 "clocks": head["clocks"], "e2e": head["e2e"], "gpu_launches": 2 * args.steps,   # per step: hc_copy_words_kernel (tile descriptors) + hc_sorted_kernel
                 "roofline": head["roofline"], "cpu_baseline": cpu,
-                "paths": {p: {k: r[k] for k in ("value", "unit", "ms_per_step", "steps", "roofline", "e2e", "workload", "clocks")} for p, r in results.items()},
+                "paths": {p: {k: r[k] for k in ("value", "unit", "ms_per_step", "steps", "roofline", "e2e", "workload", "clocks", "kernel_ms_this_rank", "drain_tail_ms_this_rank")} for p, r in results.items()},
                 "strong": strong,
                 "stats": head["stats"], "ms_steps": head["ms_steps"], "wall_s_timed_loop": head["wall"], "gen_s": head["t_gen"]}
         print(json.dumps(line), file=_RESULT_OUT, flush=True)

@@ -218,6 +218,11 @@ int hc_selftest_log10(const double* x, double* y, int* bad, long long n);
  * compile-time constant (TCOOLMAX - TCOOLMIN) / NCOOLTAB): y[i] = x[i] / DELTA_T for n HOST doubles, evaluated on the device */
 int hc_selftest_div_delta_t(const double* x, double* y, long long n);
 
+/* Device-side timing of the calling thread's most recent hc_integrate_*[_batch] launch that returned statistics (stats != NULL), from
+ * %globaltimer: kernel_ms = first CTA start -> last CTA exit; drain_ms = first time a warp found the work queue empty -> last CTA exit (the tail
+ * in which the SMs run out of cells one after the other: what strong scaling over many GPUs exposes) */
+int hc_last_launch_timing(double* kernel_ms, double* drain_ms);
+
 /* blocks until work queued on `stream` is done (cudaStreamSynchronize) */
 int hc_sync(void* stream);
 

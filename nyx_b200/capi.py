@@ -122,6 +122,7 @@ def declare(lib, prefix="hc_"):
     lib.hc_measure_fp64_peak.argtypes = [_dp]
     lib.hc_selftest_log10.argtypes = [_dp, _dp, C.POINTER(C.c_int), C.c_longlong]
     lib.hc_selftest_div_delta_t.argtypes = [_dp, _dp, C.c_longlong]
+    lib.hc_last_launch_timing.argtypes = [_dp, _dp]
     lib.hc_sync.argtypes = [C.c_void_p]
     return lib
 
@@ -280,6 +281,12 @@ class NyxHC:
         y = np.empty_like(x)
         self.check(self.lib.hc_selftest_div_delta_t(x.ctypes.data_as(_dp), y.ctypes.data_as(_dp), x.size))
         return y
+
+    def last_launch_timing(self):
+        """(kernel_ms, drain_ms) of this thread's last integrate_* launch that returned statistics"""
+        k, d = C.c_double(0.0), C.c_double(0.0)
+        self.check(self.lib.hc_last_launch_timing(C.byref(k), C.byref(d)))
+        return k.value, d.value
 
     def sync(self, stream=None):
         self.check(self.lib.hc_sync(stream))

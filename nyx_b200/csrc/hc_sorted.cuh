@@ -148,6 +148,7 @@ __global__ void __launch_bounds__(LANES, HC_SORTED_CTAS) hc_sorted_kernel(const 
     const Tables tb{a.ionx, a.iony, a.cool, a.logtab};   // all three in global memory (L1/L2)
     const Consts& c = a.k;
 
+    if (a.timing && tid == 0) atomicMax(&a.timing[2], ~global_ns());
     if (tid < P_COUNT) s_pair[tid] = 0ull;
     if (lane_id < 6) s_chunk[warp][lane_id] = 0;
     si[LaneT::WS_W0 * LANES + tid] = PC_IDLE;
@@ -237,7 +238,11 @@ __global__ void __launch_bounds__(LANES, HC_SORTED_CTAS) hc_sorted_kernel(const 
                             unsigned long long chunk = 0;
                             if (lane_id == 0) chunk = atomicAdd(a.queue, 1ull);
                             chunk = __shfl_sync(0xffffffffu, chunk, 0);
-                            if (chunk >= (unsigned long long)a.nchunks) { queue_empty = true; break; }
+                            if (chunk >= (unsigned long long)a.nchunks) {
+                                queue_empty = true;
+                                if (a.timing && lane_id == 0) atomicMax(&a.timing[0], ~global_ns());   // the drain tail starts here
+                                break;
+                            }
                             w_tile = find_tile_by_chunk(a.tiles, a.ntiles, (long long)chunk);
                             const TileDesc& t = a.tiles[w_tile];
                             const unsigned local = (unsigned)((long long)chunk - t.chunk_begin);
@@ -362,6 +367,7 @@ __global__ void __launch_bounds__(LANES, HC_SORTED_CTAS) hc_sorted_kernel(const 
 #endif
 
     flush_totals(tot, a.dstats);
+    if (a.timing && tid == 0) atomicMax(&a.timing[1], global_ns());
 }
 
 }  // namespace sorted

@@ -89,6 +89,8 @@ struct KernelArgs {
     long long nchunks;
     unsigned long long* queue;
     unsigned long long* dstats;   // HcStats as 14 x u64
+    unsigned long long* timing;   // [0] ~(first time a warp found the work queue empty) [1] last CTA exit [2] ~(first CTA start), %globaltimer ns
+                                  // (complemented values under atomicMax: the scratch is zero-initialised); nullptr: not recorded
     HcCellStat* cell_stats;
     const double* ionx;
     const double* iony;
@@ -279,6 +281,12 @@ __device__ __forceinline__ void store_cell_packed(const LaneT& ln, const KernelA
     store_cell(ln, a, a.tiles[tile], i, j, k, tot);
 }
 
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
 __device__ __noinline__ void flush_totals(const Totals& tot, unsigned long long* dstats) {
     // once per thread at the end of the kernel: the per-round counters join the CTA's packed totals, then one global atomic per counter per CTA
     // (per-CTA 32-bit halves: 134 M cells over 148 CTAs x ~35 Newton iterations per cell = 3e7)
@@ -461,6 +469,7 @@ __global__ void hc_divdelta_selftest_kernel(const double* x, double* y, long lon
 
 // ---------------------------------------------------------------------------------------------- host state
 thread_local char g_err[512] = "";
+thread_local double g_last_kernel_ms = 0.0, g_last_drain_ms = 0.0;
 void set_err(const char* fmt, ...) {
     va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof g_err, fmt, ap); va_end(ap);
 }
@@ -580,8 +589,9 @@ TileDesc make_tile(const HcFab* const* fabs, int nf, int idx, const HcBox& b, lo
     t.offset = offset;
     t.chunk_begin = chunk_begin;
     if (t.nx > 0) {
-        // a chunk is a piece of one x-row: rows longer than CHUNK_MAX are cut into equal pieces
-        t.cpr = (t.nx + CHUNK_MAX - 1) / CHUNK_MAX;
+        // a chunk is a piece of one x-row: rows longer than CHUNK_MAX are cut into equal pieces (NYX_HC_CHUNK: measurement knob)
+        static const int chunk_max = [] { const char* e = std::getenv("NYX_HC_CHUNK"); const int v = e ? std::atoi(e) : 0; return v > 0 ? v : CHUNK_MAX; }();
+        t.cpr = (t.nx + chunk_max - 1) / chunk_max;
         t.chunk_len = (t.nx + t.cpr - 1) / t.cpr;
     }
     return t;
@@ -659,6 +669,7 @@ int launch(int path, int ntiles, const HcFab* const* fabs, int nf, const HcBox* 
     a.nchunks = nchunks;
     a.queue = reinterpret_cast<unsigned long long*>(scratch);
     a.dstats = ext_dstats ? ext_dstats : reinterpret_cast<unsigned long long*>(scratch + 64);
+    a.timing = (stats && !ext_dstats) ? reinterpret_cast<unsigned long long*>(scratch + 192) : nullptr;
     a.cell_stats = cell_stats;
     a.ionx = dt.ionx; a.iony = dt.iony; a.cool = dt.cool; a.logtab = dt.logtab;
     if (eos) { a.eos_mode = eos->mode; a.max_temp_dt = eos->max_temp_dt; a.interp = eos->interp; a.small_temp = eos->small_temp; a.large_temp = eos->large_temp; }
@@ -686,7 +697,15 @@ int launch(int path, int ntiles, const HcFab* const* fabs, int nf, const HcBox* 
     if (stats && !ext_dstats) {
         // the pageable `stats` target makes this copy synchronous with respect to the host
         CUDA_TRY(cudaMemcpyAsync(stats, scratch + 64, sizeof(HcStats), cudaMemcpyDeviceToHost, stream));
+        unsigned long long tm[3] = {0, 0, 0};
+        CUDA_TRY(cudaMemcpyAsync(tm, scratch + 192, sizeof tm, cudaMemcpyDeviceToHost, stream));
         CUDA_TRY(cudaStreamSynchronize(stream));
+        if (path == PATH_VEC || path == PATH_STRUCT) {
+            // kernel span and drain tail (first "work queue empty" -> last CTA exit) of this launch, for hc_last_launch_timing
+            const unsigned long long t_empty = ~tm[0], t_end = tm[1], t_start = ~tm[2];
+            g_last_kernel_ms = (t_end > t_start) ? 1e-6 * (double)(t_end - t_start) : 0.0;
+            g_last_drain_ms = (tm[0] != 0 && t_end > t_empty) ? 1e-6 * (double)(t_end - t_empty) : 0.0;
+        }
     }
     CUDA_TRY(cudaFreeAsync(scratch, stream));
     return HC_OK;
@@ -1397,6 +1416,12 @@ int hc_selftest_div_delta_t(const double* x, double* y, long long n) {
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpy(y, dy, n * sizeof(double), cudaMemcpyDeviceToHost));
     cudaFree(dx); cudaFree(dy);
+    return HC_OK;
+}
+
+int hc_last_launch_timing(double* kernel_ms, double* drain_ms) {
+    if (kernel_ms) *kernel_ms = g_last_kernel_ms;
+    if (drain_ms) *drain_ms = g_last_drain_ms;
     return HC_OK;
 }
 

@@ -46,9 +46,13 @@ for r in rows[2:]:
     src = re.sub(r"^@!?U?P\d+\s+", "", src)
     op = src.split()[0] if src else "?"
     n = int(r[iI] or 0)
-    grp = "R" if any(k in reg for k in ("fdiv", "ion_", "iterate_ne", "rhs_tail", "eval_request", "amrex_max0", "uvb_rho")) else ("S" if ("phase S" in reg or "sort_key" in reg) else "B")
+    grp = "R" if any(k in reg for k in ("fdiv", "ion_", "iterate_ne", "rhs_tail", "eval_request", "amrex_max0", "uvb_rho", "fast_log10", "div_delta_t", "load_request", "save_result", "sm_32_intrinsics", "phase R")) else ("S" if ("phase S" in reg or "sort_key" in reg) else "B")
     mix[grp][cls(op)] += n; tot[grp] += n; samp[grp] += int(r[iS] or 0)
 T = sum(tot.values()); ST = sum(samp.values())
+thr = defaultdict(int)
+for r in rows[2:]:
+    if not r or r[0] == "Kernel Name": break
+print(f"# instruction mix by phase of {os.path.basename(rep)}: R = evaluation (RHS / EOS), B = bookkeeping (BDF state machine, load / store of cells), S = sort")
 for g in sorted(mix):
     print(f"== group {g}: warp-inst {tot[g]} ({100*tot[g]/T:.1f}% of kernel), samples {100*samp[g]/ST:.1f}%")
     for c, n in sorted(mix[g].items(), key=lambda kv: -kv[1])[:14]:
