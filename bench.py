@@ -247,7 +247,7 @@ def run_reference_arm(args):
     per_step = min(12.0, max(4.0, 240.0 / max(1, args.steps + args.warmup)))
     vals, info, cal = [], None, None
     for s in range(args.warmup + args.steps):
-        v, info = cpu_reference_run(args, args.path, idx, boxes, per_step, min_boxes=2, calibrated=cal)
+        v, info = cpu_reference_run(args, args.path, idx, boxes, per_step, min_boxes=6, calibrated=cal)
         cal = info["calibrated"]
         if s >= args.warmup:
             vals.append(v)

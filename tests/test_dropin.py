@@ -124,6 +124,38 @@ def test_dropin_use_typical_steps_updates_max_steps(dropin):
 
 
 @pytest.mark.gpu
+def test_dropin_grownvec_typical_steps_counter(dropin, reference):
+    """nyx.use_typical_steps = 1 on the FIRST Strang half-step (integrate_state_grownvec): the reference caps the step with dt / old_max_sundials_steps
+    and writes the largest step count back into OLD_max_sundials_steps (integrate_state_vec_3d.cpp:376,392) -- the counter the checkpoint files carry --
+    while integrate_state_vec works on new_max_sundials_steps (:53,67).  Same driver call against the reference build and the drop-in."""
+    z, n, ng = 3.0, 12, 2
+    a, dt = 1.0 / (1.0 + z), 0.5 * synth.step_dt(z)
+    seen = {}
+    for name, impl in (("ref", reference), ("b200", dropin)):
+        impl.set("nyx.use_typical_steps", 1)
+        try:
+            for grown in (True, False):
+                impl.set("nyx.old_max_sundials_steps", 5)
+                impl.set("nyx.new_max_sundials_steps", 7)
+                boxes, S, D = _boxes_with_ghosts(n, ng, ng, z, (531,))
+                assert impl.integrate_state_vec(boxes, S, D, a, dt, ng_state=ng, ng_diag=ng, grown=grown) == 0
+                seen[(name, grown)] = (impl.lib.nyxref_get_max_steps(0), impl.lib.nyxref_get_max_steps(1), S[0][5].copy())
+        finally:
+            impl.set("nyx.use_typical_steps", 0)
+            impl.set("nyx.old_max_sundials_steps", 3)
+            impl.set("nyx.new_max_sundials_steps", 3)
+    for name in ("ref", "b200"):
+        old_g, new_g, _ = seen[(name, True)]
+        old_v, new_v, _ = seen[(name, False)]
+        assert new_g == 7 and old_g > 5, (name, old_g, new_g)      # grownvec: the OLD counter moved (step cap dt / 5), the new one did not
+        assert old_v == 5 and new_v > 7, (name, old_v, new_v)      # vec: the NEW counter moved (step cap dt / 7)
+    # the step cap enters the integration (hmax = dt / store_steps): both builds see the same cap, so the results agree to the coupled-vs-per-cell contract
+    for grown in (True, False):
+        rel = np.abs(seen[("b200", grown)][2] / seen[("ref", grown)][2] - 1)
+        assert np.percentile(rel, 99.9) < 1e-3 and rel.max() < 3e-3
+
+
+@pytest.mark.gpu
 def test_dropin_eos_rows_vs_reference(dropin, reference):
     """SURVEY 8f rank 1 through the C++ drop-in (host FABs with ghost cells, staged by the *_host entry points): reset_internal_energy
     bit for bit, compute_new_temp to the tight EOS tolerance."""
