@@ -269,7 +269,7 @@ def run_reference_arm(args):
 COMPS = {"vec": {"state": 6, "diag": 2}, "struct": {"state": 6, "diag": 2, "s_new": 6, "hydro_src": 6, "reset_src": 1, "ir": 1}}
 MUTATED = {"vec": ("state", "diag"), "struct": ("s_new", "diag", "ir")}
 # what hc_integrate_*_host moves per cell (components of 8 bytes): Strang: rho, rho_E, rho_e in, rho_E, rho_e, T, Ne out (diag is a pure output)
-H2D_COMPS = {"vec": 3, "struct": 3 + 2 + 3 + 2 + 1 + 1}
+H2D_COMPS = {"vec": 3, "struct": 2 + 2 + 3 + 2 + 1}      # S_old(rho, rho e), diag(T, Ne), S_new(rho, rho E, rho e), hydro_src(rho, rho e), reset_src; I_R is a pure output
 D2H_COMPS = {"vec": 4, "struct": 2 + 1 + 2}
 
 
@@ -428,7 +428,7 @@ class PathBench:
         t = ctx["allmax"](t)
         return {"value": ncell_global * n / t, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": n,
                 "ms_per_step": 1e3 * t / n, "h2d_gbs_this_rank": h2d * n / t_loc / 1e9, "d2h_gbs_this_rank": d2h * n / t_loc / 1e9,
-                "api": "hc_integrate_%s_host on pinned host FABs (H2D / kernel / D2H pipelined over 8 groups of boxes)" % self.path,
+                "api": "hc_integrate_%s_host on pinned host FABs (H2D / kernel / D2H pipelined over 8 groups of boxes, kernels of consecutive groups on alternating streams)" % self.path,
                 "n_failed": st_h.n_failed}
 
     def free(self):

@@ -712,8 +712,10 @@ int launch(int path, int ntiles, const HcFab* const* fabs, int nf, const HcBox* 
 }
 
 // ---- host-buffer entry points: staged and pipelined --------------------------------------------------------------------
-// The tiles are cut into groups; group g+1 is copied to the device (stream h2d) while group g is integrated (stream comp) and
-// group g-1 is copied back (stream d2h): except for the first H2D and the last D2H the transfers hide behind the kernel.
+// The tiles are cut into groups; group g+1 is copied to the device (stream h2d) while group g is integrated (streams comp / comp2,
+// alternating) and group g-1 is copied back (stream d2h): except for the first H2D and the last D2H the transfers hide behind the kernel.
+// Consecutive groups run on two different compute streams so that the CTAs of kernel g+1 move onto the multiprocessors as the CTAs of
+// the persistent kernel g run out of work: its drain tail (~1.8 ms) overlaps the next kernel instead of idling the device once per group.
 // Device buffers come from the stream-ordered pool (its release threshold is raised once, so that repeated calls do not
 // re-acquire memory from the driver).
 struct HostSlot {
@@ -721,7 +723,7 @@ struct HostSlot {
     std::vector<int> in, out;   // components copied to the device before / back to the host after the kernel
 };
 struct HostPipe {
-    cudaStream_t h2d = nullptr, comp = nullptr, d2h = nullptr;
+    cudaStream_t h2d = nullptr, comp = nullptr, comp2 = nullptr, d2h = nullptr;
     bool ready = false;
     // Three persistent device slabs, used round-robin by the groups of a call: one copying in, one computing, one copying out.  A slab is
     // handed to group g once the D2H of group g-3 has finished (event, waited for by the h2d STREAM: the host never blocks).  No allocator in
@@ -735,7 +737,11 @@ struct HostPipe {
     std::mutex call_mu;   // host-buffer calls on one device run one after the other (they share the slabs and the three streams)
 };
 HostPipe g_pipe[64];
-constexpr int HOST_GROUPS = 8;
+#if !defined(HC_HOST_GROUPS)
+#define HC_HOST_GROUPS 8
+#endif
+constexpr int HOST_GROUPS = HC_HOST_GROUPS;
+// measurement knob: NYX_HC_HOST_ONE_COMP_STREAM=1 puts every group's kernel on the same stream (the round-1 pipeline)
 #if !defined(HC_HOST_TAPER)
 #define HC_HOST_TAPER 1
 #endif
@@ -748,6 +754,7 @@ int host_pipe(int dev, HostPipe*& hp) {
     if (!hp->ready) {
         CUDA_TRY(cudaStreamCreateWithFlags(&hp->h2d, cudaStreamNonBlocking));
         CUDA_TRY(cudaStreamCreateWithFlags(&hp->comp, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&hp->comp2, cudaStreamNonBlocking));
         CUDA_TRY(cudaStreamCreateWithFlags(&hp->d2h, cudaStreamNonBlocking));
         cudaMemPool_t pool;
         CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, dev));
@@ -792,7 +799,7 @@ struct HostCallGuard {
     explicit HostCallGuard(HostPipe* p) : hp(p) {}
     ~HostCallGuard() {
         // drain the three streams first: the slabs and the events may still be in use by queued work
-        cudaStreamSynchronize(hp->h2d); cudaStreamSynchronize(hp->comp); cudaStreamSynchronize(hp->d2h);
+        cudaStreamSynchronize(hp->h2d); cudaStreamSynchronize(hp->comp); cudaStreamSynchronize(hp->comp2); cudaStreamSynchronize(hp->d2h);
         for (int i = 0; i < HostPipe::NSLAB; ++i) hp->slab_busy[i] = false;
         if (dstats) cudaFreeAsync(dstats, hp->comp);
         for (cudaEvent_t e : events) cudaEventDestroy(e);
@@ -846,6 +853,11 @@ int run_host(int path, int ntiles, std::vector<HostSlot>& slots, const HcBox* ti
     CUDA_TRY(cudaMallocAsync((void**)&guard.dstats, 128, hp->comp));
     unsigned long long* dstats = guard.dstats;
     CUDA_TRY(cudaMemsetAsync(dstats, 0, 128, hp->comp));
+    static const bool one_comp_stream = [] { const char* e = std::getenv("NYX_HC_HOST_ONE_COMP_STREAM"); return e && std::atoi(e) != 0; }();
+    cudaEvent_t e_zero, e_last2 = nullptr;
+    CUDA_TRY(guard.new_event(e_zero));
+    CUDA_TRY(cudaEventRecord(e_zero, hp->comp));
+    CUDA_TRY(cudaStreamWaitEvent(hp->comp2, e_zero, 0));     // the statistics block is cleared before either stream's first kernel
     int rc = HC_OK;
     std::vector<std::vector<HcFab>> dfab(nf);
     int group = 0;
@@ -891,14 +903,17 @@ int run_host(int path, int ntiles, std::vector<HostSlot>& slots, const HcBox* ti
         }
         cudaEvent_t e_in, e_k;
         CUDA_TRY(guard.new_event(e_in)); CUDA_TRY(guard.new_event(e_k));
+        // custom launchers (the two-pass source assembly) order their groups through one stream
+        cudaStream_t cs = ((group & 1) && !one_comp_stream && !custom) ? hp->comp2 : hp->comp;
         CUDA_TRY(cudaEventRecord(e_in, hp->h2d));
-        CUDA_TRY(cudaStreamWaitEvent(hp->comp, e_in, 0));
+        CUDA_TRY(cudaStreamWaitEvent(cs, e_in, 0));
         std::vector<const HcFab*> fabs(nf);
         for (int s = 0; s < nf; ++s) fabs[s] = dfab[s].data();
-        rc = custom ? (*custom)(n, fabs.data(), tiles + t0, hp->comp)
-                    : launch(path, n, fabs.data(), nf, tiles + t0, k, nullptr, nullptr, hp->comp, dstats, eos);
+        rc = custom ? (*custom)(n, fabs.data(), tiles + t0, cs)
+                    : launch(path, n, fabs.data(), nf, tiles + t0, k, nullptr, nullptr, cs, dstats, eos);
         if (rc != HC_OK) break;
-        CUDA_TRY(cudaEventRecord(e_k, hp->comp));
+        CUDA_TRY(cudaEventRecord(e_k, cs));
+        if (cs == hp->comp2) e_last2 = e_k;
         CUDA_TRY(cudaStreamWaitEvent(hp->d2h, e_k, 0));
         for (int s = 0; s < nf; ++s)
             for (int i = 0; i < n; ++i) {
@@ -918,7 +933,10 @@ int run_host(int path, int ntiles, std::vector<HostSlot>& slots, const HcBox* ti
         hp->slab_busy[b] = true;
         t0 = t1;
     }
-    if (rc == HC_OK && stats) CUDA_TRY(cudaMemcpyAsync(stats, dstats, sizeof(HcStats), cudaMemcpyDeviceToHost, hp->comp));
+    if (rc == HC_OK && stats) {
+        if (e_last2) CUDA_TRY(cudaStreamWaitEvent(hp->comp, e_last2, 0));
+        CUDA_TRY(cudaMemcpyAsync(stats, dstats, sizeof(HcStats), cudaMemcpyDeviceToHost, hp->comp));
+    }
     return rc;   // the guard drains the streams and releases the scratch
 }
 
@@ -1180,12 +1198,12 @@ int hc_integrate_struct_host(int ntiles, const HcFab* s_old, const HcFab* diag, 
     const Consts k = make_consts_struct(rates_sp->data(), *prm, a, a_end, dt, sdc_iter);
     const bool src = (sdc_iter >= 0);   // with sdc_iter < 0 the update goes to S_old (f_rhs_struct.H:430-444 mirrored in store_cell)
     std::vector<HostSlot> slots = {
-        {s_old, {DENS, EDEN, EINT}, src ? std::vector<int>{} : std::vector<int>{EDEN, EINT}},
+        {s_old, src ? std::vector<int>{DENS, EINT} : std::vector<int>{DENS, EDEN, EINT}, src ? std::vector<int>{} : std::vector<int>{EDEN, EINT}},   // with sources S_old is read-only and its (rho E) is never read
         {diag, prm->inhomo_reion ? std::vector<int>{TEMP, NE, ZHI} : std::vector<int>{TEMP, NE}, {TEMP, NE}},
         {s_new, {DENS, EDEN, EINT}, src ? std::vector<int>{EDEN, EINT} : std::vector<int>{}},
         {hydro_src, {DENS, EINT}, {}},
         {reset_src, {0}, {}},
-        {ir, src ? std::vector<int>{0} : std::vector<int>{}, src ? std::vector<int>{0} : std::vector<int>{}}};   // in as well: whole components travel back, the ghost cells must keep their values
+        {ir, {}, src ? std::vector<int>{0} : std::vector<int>{}}};   // pure output: only the tile's cells travel back (copy_tile_d2h), host ghost cells keep their values
     return run_host(PATH_STRUCT, ntiles, slots, tiles, k, stats);
 }
 

@@ -21,7 +21,8 @@ pytestmark = pytest.mark.gpu
 
 E_T_TOL = 1e-3        # the contract: 10 x rtol
 E_T_TIGHT = 1e-5      # cells that follow the same step sequence as the oracle (measured: <= 1e-6, median 0: ~50 % bitwise)
-EXACT_FRACTION = 0.999
+EXACT_FRACTION = 0.999      # struct (SDC) cases, 13824 cells each: measured 0.99928 .. 1.0 (profiles/r2_s12_pytest.log)
+EXACT_FRACTION_VEC = 0.9999  # Strang cases: measured 1.0 in every case (3 cells of 32768 allowed)
 
 
 def _torch():
@@ -47,14 +48,14 @@ def _compare_counts(cs, pst, what, chaotic_cells=0, need=None):
     fail_diff = np.flatnonzero((cs["flag"] < 0) != (pst[:, 7] < 0))
     assert len(fail_diff) <= chaotic_cells, f"{what}: failed cells differ at {fail_diff[:8]}: gpu {cs['flag'][fail_diff[:8]]} oracle {pst[fail_diff[:8], 7]}"
     assert abs(int((cs["flag"] < 0).sum()) - int((pst[:, 7] < 0).sum())) <= chaotic_cells
-    assert len(bad) <= max(1, chaotic_cells, len(cs) // 2000), f"{what}: CVODE flags differ in {len(bad)} cells: gpu {cs['flag'][bad[:8]]} oracle {pst[bad[:8], 7]}"
+    assert len(bad) <= max(1, chaotic_cells), f"{what}: CVODE flags differ in {len(bad)} cells: gpu {cs['flag'][bad[:8]]} oracle {pst[bad[:8], 7]}"
     same = np.ones(len(cs), dtype=bool)
     for i, f in enumerate(capi.CELLSTAT_FIELDS[:7]):
         same &= cs[f] == pst[:, i]
     frac = same.mean()
     # in the stress case the thrashing cells (dozens of error-test failures each) amplify every last-bit difference -- e.g. the
     # device takes x^(1/3) with cbrt(), glibc with pow(x, 0.333..) -- into different counters: 1 % of its cells
-    need = need or (0.98 if chaotic_cells else EXACT_FRACTION)
+    need = need or (0.99 if chaotic_cells else EXACT_FRACTION)      # stress case measured: 0.9919
     print(f"\n[parity] {what}: identical counters {int(same.sum())}/{len(same)} ({frac:.6f}), flags differ in {len(bad)} cells, failed gpu {int((cs['flag'] < 0).sum())} oracle {int((pst[:, 7] < 0).sum())}")
     assert frac >= need, f"{what}: only {frac:.5f} of cells have identical counters"
     return same
@@ -123,7 +124,7 @@ def test_vec_matches_oracle(hc_lib, port, z, n, seed):
     for comp in (0, 1, 2, 3):
         assert np.array_equal(s_gpu[comp], state[comp])          # untouched components stay bit-identical
     cs = _cs_to_numpy(csb)
-    same = _compare_counts(cs, pst, f"vec z={z}").reshape(n, n, n)
+    same = _compare_counts(cs, pst, f"vec z={z}", need=EXACT_FRACTION_VEC).reshape(n, n, n)
     e_rel, E_rel, T_rel = _rel(s_gpu[5], s_ref[5]), _rel(s_gpu[4], s_ref[4]), _rel(d_gpu[0], d_ref[0])
     ne_abs = np.abs(d_gpu[1] - d_ref[1])
     assert max(e_rel.max(), E_rel.max(), T_rel.max()) < E_T_TOL
@@ -181,13 +182,13 @@ def test_struct_matches_oracle(hc_lib, port, z, seed, src, flash):
     # finite-difference probe of the diagonal Jacobian at y + 0.1*rl1*(h*f - zn[1]) (cvode_diag.c:364), whose offset is a
     # cancellation residue: a last-bit difference in f moves it by O(1), so this diagnostic T differs by up to ~1e-4
     # (1e-2 in cells that cooled to a few K) between any two libm's even when every integrator decision is identical.
-    # (measured: up to 5 % of the cells of the z = 2 case beyond 1e-3).  Held to: median agreement at round-off level; and the T the caller's next compute_new_temp
+    # (measured: up to 3.7 % of the cells -- the H I flash case -- beyond 1e-3).  Held to: median agreement at round-off level; and the T the caller's next compute_new_temp
     # derives from the updated state (tested below through the EOS kernel) to the tight bound.
     T_rel = _rel(out["diag"][0], ref["diag"][0])
     ne_abs = np.abs(out["diag"][1] - ref["diag"][1])
     print(f"[parity] struct z={z} {flash}: diag T of the last RHS evaluation beyond 1e-3 in {np.mean(T_rel[m] > E_T_TOL):.4f} of the same-sequence cells, Ne in {np.mean(ne_abs[m] > E_T_TOL):.4f}")
-    assert np.median(T_rel[m]) < 1e-9 and np.mean(T_rel[m] > E_T_TOL) < 0.2, (np.median(T_rel[m]), np.mean(T_rel[m] > E_T_TOL))
-    assert np.median(ne_abs[m]) < 1e-9 and np.mean(ne_abs[m] > E_T_TOL) < 0.2
+    assert np.median(T_rel[m]) < 1e-9 and np.mean(T_rel[m] > E_T_TOL) < 0.06, (np.median(T_rel[m]), np.mean(T_rel[m] > E_T_TOL))
+    assert np.median(ne_abs[m]) < 1e-9 and np.mean(ne_abs[m] > E_T_TOL) < 2e-3      # measured: T <= 3.7 % (H I flash case), Ne <= 1e-4
     # T, ne recomputed from the updated state (what Nyx::compute_new_temp does right after, Nyx_advance.cpp:374-376)
     hc_lib.eos_T_given_Re(capi.fab_of_torch(dev["s_new"], lo), capi.fab_of_torch(dev["diag"], lo), capi.make_box(lo, hi), d["a_end"])
     torch.cuda.synchronize()
@@ -439,7 +440,9 @@ def test_ragged_and_empty_batches(hc_lib, port):
     off = 0
     for s_ref, d_ref, pst, s_dev, d_dev in refs:
         n = len(pst)
-        assert np.array_equal(cs["nst"][off:off + n], pst[:, 0]) or np.mean(cs["nst"][off:off + n] == pst[:, 0]) > 0.99
+        same_nst = np.mean(cs["nst"][off:off + n] == pst[:, 0])
+        print(f"[parity] ragged batch box of {n} cells: identical nst {same_nst:.6f}")
+        assert same_nst >= EXACT_FRACTION_VEC or (n < 10000 and (1 - same_nst) * n <= 1)
         assert np.abs(s_dev.cpu().numpy()[5] / s_ref[5] - 1).max() < E_T_TOL and np.abs(d_dev.cpu().numpy()[0] / d_ref[0] - 1).max() < E_T_TOL
         off += n
     assert st.sum_nst == int(cs["nst"].sum())

@@ -304,3 +304,26 @@ def test_two_rank_stats_allreduce_gloo(tmp_path):
     outs = [p.communicate(timeout=180)[0].decode() for p in procs]
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0 and f"ok {r}" in o, o
+
+
+def test_bench_reference_arm_line(built):
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the GPU arm): one JSON line, the same metric / unit / config keys as the GPU
+    arm's line (so that the driver's same-config check holds), min / median / max of the timed samples, host threads counted before libgomp binds"""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--n", "32", "--box", "16", "--steps", "2", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=600, env=dict(os.environ, OMP_NUM_THREADS="1"))
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "heatcool_cell_updates_per_s" and d["unit"] == "cell-updates/s" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["gpu_launches"] == 0
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["min"] <= cb["median"] <= cb["max"] and cb["value"] == d["value"]
+    assert cb["cores"] == len(os.sched_getaffinity(0))      # torchrun's OMP_NUM_THREADS=1 does not pin the reference to one thread
+    # the keys the GPU arm writes into `config` (bench.py: config_of)
+    for k in ("workload", "cells_per_gpu", "boxes_per_gpu", "path", "z", "rtol", "atol_factor", "parallelism"):
+        assert k in d["config"], k
+    assert d["config"]["path"] == "vec" and d["config"]["cells_per_gpu"] == 32 ** 3
