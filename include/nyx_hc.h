@@ -136,6 +136,24 @@ int hc_integrate_struct_batch(int ntiles, const HcFab* s_old, const HcFab* diag,
                               const HcFab* reset_src, const HcFab* ir, const HcBox* tiles, double a, double a_end, double dt,
                               int sdc_iter, const HcParams* prm, HcStats* stats, HcCellStat* cell_stats, void* stream);
 
+/* The SAVE_REACT overload of Nyx::integrate_state_struct_mfin (Source/Driver/Nyx.H:571-580, integrate_state_with_source_3d.cpp:126-183,
+ * 602-631; compiled with USE_SAVE_REACT = TRUE, Exec/Make.Nyx:51-52): the same integration, and per cell the three diagnostic FABs that
+ * ode_eos_save_react_arrays (f_rhs_struct.H:213-267) fills right after the finalize step:
+ *   react_in (7 components)        e(t0), rho(t0), rhoe_src, e_src, abstol, a, 0
+ *   react_out (7)                  CVODE's solution (before the finalize step's floor / heating), rho(t0) + dt * rho_src, T and ne after the
+ *                                  finalize step's last EOS solve, CVodeGetEstLocalErrors, a_end, dt
+ *   react_out_work (9)             nst, netf, nfe, nni, ncfn, nsetups, 0, 0, nfeLS -- of the CELL (the reference reports the counters of the
+ *                                  tile-wide CVODE instance in every cell of the tile; its nje / ncfl are never assigned)
+ * Needs the SDC sources (sdc_iter >= 0: without them the reference reads null pointers here).  The caller writes the plotfiles. */
+int hc_integrate_struct_react_batch(int ntiles, const HcFab* s_old, const HcFab* diag, const HcFab* s_new, const HcFab* hydro_src,
+                                    const HcFab* reset_src, const HcFab* ir, const HcFab* react_in, const HcFab* react_out,
+                                    const HcFab* react_out_work, const HcBox* tiles, double a, double a_end, double dt, int sdc_iter,
+                                    const HcParams* prm, HcStats* stats, HcCellStat* cell_stats, void* stream);
+int hc_integrate_struct_react_host(int ntiles, const HcFab* s_old, const HcFab* diag, const HcFab* s_new, const HcFab* hydro_src,
+                                   const HcFab* reset_src, const HcFab* ir, const HcFab* react_in, const HcFab* react_out,
+                                   const HcFab* react_out_work, const HcBox* tiles, double a, double a_end, double dt, int sdc_iter,
+                                   const HcParams* prm, HcStats* stats);
+
 /* compute_new_temp core: diag(Temp,Ne) = EOS(state(Density), state(Eint)/state(Density), a) with JH = JHe = 1 */
 int hc_eos_T_given_Re(const HcFab* state, const HcFab* diag, HcBox tile, double a, const HcParams* prm, HcStats* stats,
                       void* stream);

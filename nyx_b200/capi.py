@@ -109,6 +109,9 @@ def declare(lib, prefix="hc_"):
     lib.hc_reset_internal_energy_host.argtypes = [C.c_int, fp, fp, fp, bp, C.c_double, pp, C.c_double, C.c_int]
     lib.hc_integrate_vec_host.argtypes = [C.c_int, fp, fp, bp, C.c_double, C.c_double, pp, sp]
     lib.hc_integrate_struct_host.argtypes = [C.c_int] + [fp] * 6 + [bp, C.c_double, C.c_double, C.c_double, C.c_int, pp, sp]
+    lib.hc_integrate_struct_react_batch.argtypes = [C.c_int] + [fp] * 9 + [bp, C.c_double, C.c_double, C.c_double, C.c_int, pp, sp,
+                                                                            C.c_void_p, C.c_void_p]
+    lib.hc_integrate_struct_react_host.argtypes = [C.c_int] + [fp] * 9 + [bp, C.c_double, C.c_double, C.c_double, C.c_int, pp, sp]
     qp = C.POINTER(HcSrcParams)
     lib.hc_default_src_params.argtypes = [qp]
     lib.hc_update_state_with_sources_batch.argtypes = [C.c_int] + [fp] * 5 + [bp, C.c_double, C.c_double, C.c_double, qp, _dp, C.c_void_p]
@@ -187,6 +190,25 @@ class NyxHC:
         arrs = [self._arr(x, HcFab) for x in (s_old, diag, s_new, hydro_src, reset_src, ir)]
         self.check(self.lib.hc_integrate_struct_batch(n, *arrs, self._arr(tiles, HcBox), a, a_end, dt, sdc_iter, C.byref(p),
                                                       C.byref(st) if want_stats else None, cell_stats_ptr, stream))
+        return st
+
+    def integrate_struct_react_batch(self, s_old, diag, s_new, hydro_src, reset_src, ir, react_in, react_out, react_out_work, tiles, a, a_end, dt,
+                                     sdc_iter=0, params=None, cell_stats_ptr=None, stream=None, want_stats=True):
+        """the SAVE_REACT overload (Nyx.H:571-580): integrate_struct_batch + the three diagnostic FABs (7, 7, 9 components)"""
+        p = params or self.default_params()
+        st = HcStats()
+        arrs = [self._arr(x, HcFab) for x in (s_old, diag, s_new, hydro_src, reset_src, ir, react_in, react_out, react_out_work)]
+        self.check(self.lib.hc_integrate_struct_react_batch(len(tiles), *arrs, self._arr(tiles, HcBox), a, a_end, dt, sdc_iter, C.byref(p),
+                                                            C.byref(st) if want_stats else None, cell_stats_ptr, stream))
+        return st
+
+    def integrate_struct_react_host(self, s_old, diag, s_new, hydro_src, reset_src, ir, react_in, react_out, react_out_work, tiles, a, a_end, dt,
+                                    sdc_iter=0, params=None):
+        p = params or self.default_params()
+        st = HcStats()
+        arrs = [self._arr(x, HcFab) for x in (s_old, diag, s_new, hydro_src, reset_src, ir, react_in, react_out, react_out_work)]
+        self.check(self.lib.hc_integrate_struct_react_host(len(tiles), *arrs, self._arr(tiles, HcBox), a, a_end, dt, sdc_iter, C.byref(p),
+                                                           C.byref(st)))
         return st
 
     def integrate_vec_host(self, state_fabs, diag_fabs, tiles, a, dt, params=None):

@@ -130,7 +130,10 @@ __device__ unsigned long long g_phase[48];
 #define HC_TICK(slot) do { } while (0)
 #endif
 
-template <int PATH, int LANES>
+// REACT (SDC path only): the instantiation behind the SAVE_REACT dumps (integrate_state_with_source_3d.cpp:126-183,602-631) also records,
+// per cell, what CVODE returned before the finalize step touched it (raw solution, estimated local error) and what the finalize step
+// left (density of the last RHS evaluation, final energy): a.react_raw, 4 doubles per cell.  The production instantiations are unchanged.
+template <int PATH, int LANES, bool REACT = false>
 __global__ void __launch_bounds__(LANES, HC_SORTED_CTAS) hc_sorted_kernel(const __grid_constant__ KernelArgs a) {
     using L = Layout<PATH, LANES>;
     using LaneT = typename L::LaneT;
@@ -218,10 +221,11 @@ __global__ void __launch_bounds__(LANES, HC_SORTED_CTAS) hc_sorted_kernel(const 
                 ln.resume(c, f, rmask);
                 if (ln.fin_pending) {
                     if (PATH == PATH_STRUCT) load_finalize_cell(ln, a, cell0, cell1);
+                    if (REACT) store_react_cvode(a, cell0, cell1, ln.e_final, ln.acor);   // dptr[idx], CVodeGetEstLocalErrors (= cv_acor, cvode_io.c:1346-1360)
                     ln.begin_finalize(c);
                 }
                 tot.iters_attempts += (unsigned long long)(unsigned)ln.attempts << 32;
-                if (!ln.active()) store_cell_packed(ln, a, cell0, cell1, tot);
+                if (!ln.active()) store_cell_packed<LaneT, REACT>(ln, a, cell0, cell1, tot);
             }
             __syncwarp();
             HC_TICK(17);
@@ -263,7 +267,10 @@ __global__ void __launch_bounds__(LANES, HC_SORTED_CTAS) hc_sorted_kernel(const 
                             load_cell(ln, a, t, c_i, w_j, w_k);
                             tot.iters_attempts += (unsigned long long)(unsigned)ln.attempts << 32;
                             if (ln.active()) { need = false; io.w(LaneT::WS_CELL0) = cell0; io.w(LaneT::WS_CELL1) = cell1; }
-                            else store_cell(ln, a, t, c_i, w_j, w_k, tot);
+                            else {
+                                if (REACT) store_react_cvode(a, cell0, cell1, ln.e0, 0.0);   // CVode refused the input: the solution vector still holds e(t0)
+                                store_cell<LaneT, REACT>(ln, a, t, c_i, w_j, w_k, tot);
+                            }
                         }
                         w_x += min(avail, __popc(m));
                         m = __ballot_sync(0xffffffffu, need);

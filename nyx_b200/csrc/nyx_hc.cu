@@ -92,6 +92,7 @@ struct KernelArgs {
     unsigned long long* timing;   // [0] ~(first time a warp found the work queue empty) [1] last CTA exit [2] ~(first CTA start), %globaltimer ns
                                   // (complemented values under atomicMax: the scratch is zero-initialised); nullptr: not recorded
     HcCellStat* cell_stats;
+    double* react_raw;            // REACT instantiation only: per cell {CVODE's solution, its estimated local error, rho of the last RHS evaluation, final e}
     const double* ionx;
     const double* iony;
     const double* cool;
@@ -242,7 +243,11 @@ __device__ __forceinline__ void prefetch_finalize_cell(const KernelArgs& a, unsi
 }
 
 // scatter a finished cell (HOT LOOP C: integrate_state_vec_3d.cpp:317-321, f_rhs_struct.H:290-291,438-444)
-template <class LaneT>
+__device__ __forceinline__ long long cell_index(const TileDesc& t, int i, int j, int k) {
+    return t.offset + ((long long)(k - t.lo[2]) * t.ny + (j - t.lo[1])) * t.nx + (i - t.lo[0]);
+}
+
+template <class LaneT, bool REACT = false>
 __device__ __forceinline__ void store_cell(const LaneT& ln, const KernelArgs& a, const TileDesc& t, int i, int j, int k, Totals& tot) {
     constexpr int PATH = LaneT::path;
     const Consts& c = a.k;
@@ -261,9 +266,10 @@ __device__ __forceinline__ void store_cell(const LaneT& ln, const KernelArgs& a,
         pn[EINT * t.f[F_SNEW].nstride] = ln.rhoe_new + d;
         pn[EDEN * t.f[F_SNEW].nstride] = pn[EDEN * t.f[F_SNEW].nstride] + d;
     }
-    if (a.cell_stats) {
-        const long long id = t.offset + ((long long)(k - t.lo[2]) * t.ny + (j - t.lo[1])) * t.nx + (i - t.lo[0]);
-        a.cell_stats[id] = HcCellStat{ln.nst, ln.netf, ln.nfe, ln.nni, ln.nnf, ln.nsetups, ln.nfe_ls, ln.flag};
+    if (a.cell_stats) a.cell_stats[cell_index(t, i, j, k)] = HcCellStat{ln.nst, ln.netf, ln.nfe, ln.nni, ln.nnf, ln.nsetups, ln.nfe_ls, ln.flag};
+    if (REACT) {
+        double* raw = a.react_raw + 4 * cell_index(t, i, j, k);
+        raw[2] = ln.lastRho; raw[3] = ln.e_final;
     }
     atomicAdd(&tot.s_pair[P_CELLS_FAILED], 1ull | ((unsigned long long)(ln.flag < 0) << 32));
     atomicAdd(&tot.s_pair[P_FLOOR_NST], (unsigned long long)(unsigned)ln.floor_hit | ((unsigned long long)(unsigned)ln.nst << 32));
@@ -274,11 +280,19 @@ __device__ __forceinline__ void store_cell(const LaneT& ln, const KernelArgs& a,
     atomicMax(&tot.s_pair[P_MAXNST], (unsigned long long)(unsigned)ln.nst);
 }
 
-template <class LaneT>
+template <class LaneT, bool REACT = false>
 __device__ __forceinline__ void store_cell_packed(const LaneT& ln, const KernelArgs& a, unsigned cell0, unsigned cell1, Totals& tot) {
     int tile, i, j, k;
     unpack_cell(a, cell0, cell1, tile, i, j, k);
-    store_cell(ln, a, a.tiles[tile], i, j, k, tot);
+    store_cell<LaneT, REACT>(ln, a, a.tiles[tile], i, j, k, tot);
+}
+
+// REACT instantiation: what CVode handed back for this cell, before ode_eos_finalize_struct
+__device__ __forceinline__ void store_react_cvode(const KernelArgs& a, unsigned cell0, unsigned cell1, double e_cvode, double ele) {
+    int tile, i, j, k;
+    unpack_cell(a, cell0, cell1, tile, i, j, k);
+    double* raw = a.react_raw + 4 * cell_index(a.tiles[tile], i, j, k);
+    raw[0] = e_cvode; raw[1] = ele;
 }
 
 __device__ __forceinline__ unsigned long long global_ns() {
@@ -375,6 +389,70 @@ __global__ void __launch_bounds__(EOS_THREADS, 1) hc_eos_kernel(const __grid_con
     if (n_large) atomicAdd(&s_stats[S_FAILED], n_large);
     __syncthreads();
     if (threadIdx.x < S_COUNT) atomicAdd(&a.dstats[threadIdx.x], s_stats[threadIdx.x]);
+}
+
+// SAVE_REACT dumps (ode_eos_save_react_arrays, f_rhs_struct.H:213-267, called right after ode_eos_finalize_struct): the three diagnostic
+// FABs react_in (7 components), react_out (7), react_out_work (9), assembled per cell from the call's inputs (S_old is read-only when
+// sdc_iter >= 0), the per-cell record of the REACT instantiation of the integrator kernel and its per-cell counters.
+//   react_in        eptr (= e(t0)), rho_init_vode, rhoe_src_vode, e_src_vode, abstol, a, time_in (= 0)
+//   react_out       dptr (CVODE's solution, untouched by the finalize step), rho_init + dt * rho_src, T_vode, ne_vode, estimated local error, a_end, dt
+//   react_out_work  nst, netf, nfe, nni, ncfn, nsetups, nje, ncfl, nfeLS -- per CELL here, per tile-wide CVODE instance in the reference; nje and ncfl are
+//                   never assigned by the reference's GetFinalStats (integrate_state_with_source_3d.cpp:792-810: uninitialised values): written as 0
+// T_vode / ne_vode after the finalize step are the EOS solve of its LAST nyx_eos_T_given_Re_device call (f_rhs_struct.H:346-348, or :423-426 after
+// instantaneous reionization heating): a function of (rho of the last RHS evaluation, final e, J_H of the cell) only -- the solve starts from
+// ne = 1 whatever the caller holds (eos_hc.H:151) -- so it is evaluated here rather than carried through the integrator kernel.
+struct ReactArgs {
+    const HcFab* rf;          // [ntiles][3]: react_in, react_out, react_out_work of each tile
+    const double* raw;        // [ncells][4]
+    const HcCellStat* cs;     // [ncells]
+};
+__global__ void __launch_bounds__(EOS_THREADS, 1) hc_react_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ ReactArgs r) {
+    double* s_ionx = reinterpret_cast<double*>(s_raw);
+    double* s_iony = reinterpret_cast<double*>(s_raw + SM_IONX);
+    stage_tables(a, s_ionx, s_iony);
+    __syncthreads();
+    const Tables tb{s_ionx, s_iony, a.cool, a.logtab};
+    const Consts& c = a.k;
+    int ti = -1;
+    for (long long id = (long long)blockIdx.x * EOS_THREADS + threadIdx.x; id < a.ncells; id += (long long)gridDim.x * EOS_THREADS) {
+        ti = next_tile(a, ti, id);
+        const TileDesc& t = a.tiles[ti];
+        int i, j, k;
+        cell_of(t, id, i, j, k);
+        // ode_eos_initialize_arrays f_rhs_struct.H:180-193, the expressions of load_cell
+        const long long so = fab_off(t.f[F_STATE], i, j, k);
+        const double rho = t.f[F_STATE].p[so + DENS * t.f[F_STATE].nstride];
+        const double rhoe0 = t.f[F_STATE].p[so + EINT * t.f[F_STATE].nstride];
+        const double e0 = rhoe0 / rho;
+        const long long ho = fab_off(t.f[F_HSRC], i, j, k);
+        const double rho_src = t.f[F_HSRC].p[ho + DENS * t.f[F_HSRC].nstride] / c.dt;
+        const double rhoe_src = t.f[F_HSRC].p[ho + EINT * t.f[F_HSRC].nstride] / c.dt;
+        const double reset_src = t.f[F_RSRC].p[fab_off(t.f[F_RSRC], i, j, k)];
+        const double e_src = (((c.asq * rhoe0 + c.dt * rhoe_src) / c.aendsq + reset_src) / (rho + c.dt * rho_src) - e0) / c.dt;
+        double jh = (double)c.JH0;
+        if (c.inhomo) jh = (c.z > t.f[F_DIAG].p[fab_off(t.f[F_DIAG], i, j, k) + ZHI * t.f[F_DIAG].nstride]) ? 0.0 : 1.0;
+        const double* raw = r.raw + 4 * id;
+        // nyx_eos_T_given_Re_device(rho_vode, e_out) eos_hc.H:190-220, as Lane::eval_request evaluates it for PC_FINAL_EOS
+        const double rho_cgs = raw[2] * density_to_cgs / c.a3_eos;
+        const double U = raw[3] * e_to_cgs;
+        const double nh = rho_cgs * c.h_species / MPROTON;
+        EosOut s;
+        iterate_ne(tb, c, c.uvb_eos, jh, (double)c.JHe0, U, nh, s);
+        const HcFab& RI = r.rf[3 * ti + 0];
+        const HcFab& RO = r.rf[3 * ti + 1];
+        const HcFab& RW = r.rf[3 * ti + 2];
+        double* pi = RI.p + fab_off(RI, i, j, k);
+        pi[0 * RI.nstride] = e0; pi[1 * RI.nstride] = rho; pi[2 * RI.nstride] = rhoe_src; pi[3 * RI.nstride] = e_src;
+        pi[4 * RI.nstride] = nv_scale(c.atol_factor, e0); pi[5 * RI.nstride] = c.a; pi[6 * RI.nstride] = 0.0;
+        double* po = RO.p + fab_off(RO, i, j, k);
+        po[0 * RO.nstride] = raw[0]; po[1 * RO.nstride] = rho + c.dt * rho_src; po[2 * RO.nstride] = s.T; po[3 * RO.nstride] = s.ne;
+        po[4 * RO.nstride] = raw[1]; po[5 * RO.nstride] = c.a_end; po[6 * RO.nstride] = c.dt;
+        const HcCellStat cs = r.cs[id];
+        double* pw = RW.p + fab_off(RW, i, j, k);
+        pw[0 * RW.nstride] = (double)cs.nst; pw[1 * RW.nstride] = (double)cs.netf; pw[2 * RW.nstride] = (double)cs.nfe; pw[3 * RW.nstride] = (double)cs.nni;
+        pw[4 * RW.nstride] = (double)cs.ncfn; pw[5 * RW.nstride] = (double)cs.nsetups; pw[6 * RW.nstride] = 0.0; pw[7 * RW.nstride] = 0.0;
+        pw[8 * RW.nstride] = (double)cs.nfe_ls;
+    }
 }
 
 // reset_internal_e (Source/EOS/reset_internal_e.H:16-68) over all tiles: synchronises (rho e) and (rho E), records the change of
@@ -481,7 +559,7 @@ struct DeviceTables {
     double* cool = nullptr;
     double* logtab = nullptr;
     int sm_count = 0;
-    std::atomic<bool> attr_set[3] = {{false}, {false}, {false}};   // set-once flags (the attribute calls themselves are idempotent)
+    std::atomic<bool> attr_set[5] = {{false}, {false}, {false}, {false}, {false}};   // set-once flags (the attribute calls themselves are idempotent)
 };
 std::mutex g_mu;
 // host copy of the rates image: replaced as a whole by hc_tables_upload under g_mu; every reader takes a reference-counted snapshot under the
@@ -629,19 +707,35 @@ struct EosOpts {
     double small_temp = 0.0, large_temp = 0.0;
 };
 constexpr int PATH_RESET_E = 3;   // hc_reset_e_kernel (PATH_EOS = 2: hc_eos_kernel)
+// the three SAVE_REACT FABs of every tile (device memory)
+struct ReactFabs {
+    const HcFab* in; const HcFab* out; const HcFab* work;
+};
 
 int launch(int path, int ntiles, const HcFab* const* fabs, int nf, const HcBox* tiles, const Consts& k, HcStats* stats,
-           HcCellStat* cell_stats, cudaStream_t stream, unsigned long long* ext_dstats = nullptr, const EosOpts* eos = nullptr) {
+           HcCellStat* cell_stats, cudaStream_t stream, unsigned long long* ext_dstats = nullptr, const EosOpts* eos = nullptr,
+           const ReactFabs* react = nullptr) {
     int dev; if (int rc = current_device(dev)) return rc;
     DeviceTables& dt = g_dev[dev];
     if (!dt.ionx) { set_err("hc_tables_upload has not been called on device %d", dev); return HC_ERR_NO_TABLES; }
     if (ntiles < 0) { set_err("ntiles < 0"); return HC_ERR_ARG; }
     std::vector<TileDesc> h_tiles; h_tiles.reserve(ntiles);
+    std::vector<HcFab> h_react;
     long long ncells = 0, nchunks = 0;
     for (int t = 0; t < ntiles; ++t) {
         TileDesc td = make_tile(fabs, nf, t, tiles[t], ncells, nchunks);
         if (td.nx <= 0 || td.ny <= 0 || td.nz <= 0) continue;   // empty tile: nothing to do (as an empty MFIter tile)
         if (!tile_inside(td, nf)) { set_err("tile %d is not contained in its FABs (or a FAB pointer is null)", t); return HC_ERR_ARG; }
+        if (react) {
+            const HcFab rf[3] = {react->in[t], react->out[t], react->work[t]};
+            const int need[3] = {7, 7, 9};
+            for (int s = 0; s < 3; ++s) {
+                bool ok = rf[s].p && rf[s].ncomp >= need[s];
+                for (int d = 0; d < 3 && ok; ++d) ok = tiles[t].lo[d] >= rf[s].lo[d] && tiles[t].hi[d] <= rf[s].hi[d];
+                if (!ok) { set_err("tile %d: react FAB %d is null, has fewer than %d components or does not contain the tile", t, s, need[s]); return HC_ERR_ARG; }
+                h_react.push_back(rf[s]);
+            }
+        }
         // a lane remembers its cell as (tile: 20 bits, k: 12 bits, i, j: 16 bits each, relative to the tile)
         if ((path == PATH_VEC || path == PATH_STRUCT) && (td.nx > 65536 || td.ny > 65536 || td.nz > 4096 || h_tiles.size() >= (1u << 20))) {
             set_err("tile %d: the integrator kernels take tiles of at most 65536 x 65536 x 4096 cells and at most 2^20 tiles per call", t); return HC_ERR_ARG;
@@ -655,11 +749,20 @@ int launch(int path, int ntiles, const HcFab* const* fabs, int nf, const HcBox* 
     if (ncells == 0) return HC_OK;
 
     const size_t tiles_bytes = h_tiles.size() * sizeof(TileDesc);
-    const size_t scratch_bytes = 256 + tiles_bytes;   // [queue u64][pad][stats 14 x u64][pad] [tiles]
+    const size_t react_bytes = h_react.size() * sizeof(HcFab);
+    const size_t scratch_bytes = 256 + tiles_bytes + react_bytes;   // [queue u64][pad][stats 14 x u64][pad] [tiles] [react FABs]
     char* scratch = nullptr;
     CUDA_TRY(cudaMallocAsync((void**)&scratch, scratch_bytes, stream));
     CUDA_TRY(cudaMemsetAsync(scratch, 0, 256, stream));
     if (int rc = copy_small_h2d(dev, scratch + 256, h_tiles.data(), tiles_bytes, stream)) return rc;
+    // SAVE_REACT: the per-cell record of the REACT kernel and (unless the caller asked for them anyway) the per-cell counters
+    double* react_raw = nullptr;
+    HcCellStat* own_cell_stats = nullptr;
+    if (react) {
+        if (int rc = copy_small_h2d(dev, scratch + 256 + tiles_bytes, h_react.data(), react_bytes, stream)) return rc;
+        CUDA_TRY(cudaMallocAsync((void**)&react_raw, (size_t)ncells * 4 * sizeof(double), stream));
+        if (!cell_stats) { CUDA_TRY(cudaMallocAsync((void**)&own_cell_stats, (size_t)ncells * sizeof(HcCellStat), stream)); cell_stats = own_cell_stats; }
+    }
 
     KernelArgs a{};
     a.k = k;
@@ -671,6 +774,7 @@ int launch(int path, int ntiles, const HcFab* const* fabs, int nf, const HcBox* 
     a.dstats = ext_dstats ? ext_dstats : reinterpret_cast<unsigned long long*>(scratch + 64);
     a.timing = (stats && !ext_dstats) ? reinterpret_cast<unsigned long long*>(scratch + 192) : nullptr;
     a.cell_stats = cell_stats;
+    a.react_raw = react_raw;
     a.ionx = dt.ionx; a.iony = dt.iony; a.cool = dt.cool; a.logtab = dt.logtab;
     if (eos) { a.eos_mode = eos->mode; a.max_temp_dt = eos->max_temp_dt; a.interp = eos->interp; a.small_temp = eos->small_temp; a.large_temp = eos->large_temp; }
 
@@ -679,6 +783,15 @@ int launch(int path, int ntiles, const HcFab* const* fabs, int nf, const HcBox* 
         const int g = (int)std::min<long long>((ncells + LV - 1) / LV, (long long)dt.sm_count * HC_SORTED_CTAS);
         if (int rc = set_smem_attr(sorted::hc_sorted_kernel<PATH_VEC, LV>, dt, 0, sorted::Layout<PATH_VEC, LV>::total)) return rc;
         sorted::hc_sorted_kernel<PATH_VEC, LV><<<g, LV, sorted::Layout<PATH_VEC, LV>::total, stream>>>(a);
+    } else if (path == PATH_STRUCT && react) {
+        const int g = (int)std::min<long long>((ncells + LS - 1) / LS, (long long)dt.sm_count * HC_SORTED_CTAS);
+        if (int rc = set_smem_attr(sorted::hc_sorted_kernel<PATH_STRUCT, LS, true>, dt, 3, sorted::Layout<PATH_STRUCT, LS>::total)) return rc;
+        sorted::hc_sorted_kernel<PATH_STRUCT, LS, true><<<g, LS, sorted::Layout<PATH_STRUCT, LS>::total, stream>>>(a);
+        CUDA_TRY(cudaGetLastError());
+        if (int rc = set_smem_attr(hc_react_kernel, dt, 4, SMEM_EOS)) return rc;
+        ReactArgs ra{reinterpret_cast<const HcFab*>(scratch + 256 + tiles_bytes), react_raw, cell_stats};
+        const int ge = (int)std::min<long long>((ncells + EOS_THREADS - 1) / EOS_THREADS, dt.sm_count);
+        hc_react_kernel<<<ge, EOS_THREADS, SMEM_EOS, stream>>>(a, ra);
     } else if (path == PATH_STRUCT) {
         const int g = (int)std::min<long long>((ncells + LS - 1) / LS, (long long)dt.sm_count * HC_SORTED_CTAS);
         if (int rc = set_smem_attr(sorted::hc_sorted_kernel<PATH_STRUCT, LS>, dt, 1, sorted::Layout<PATH_STRUCT, LS>::total)) return rc;
@@ -707,6 +820,8 @@ int launch(int path, int ntiles, const HcFab* const* fabs, int nf, const HcBox* 
             g_last_drain_ms = (tm[0] != 0 && t_end > t_empty) ? 1e-6 * (double)(t_end - t_empty) : 0.0;
         }
     }
+    if (react_raw) CUDA_TRY(cudaFreeAsync(react_raw, stream));
+    if (own_cell_stats) CUDA_TRY(cudaFreeAsync(own_cell_stats, stream));
     CUDA_TRY(cudaFreeAsync(scratch, stream));
     return HC_OK;
 }
@@ -812,7 +927,8 @@ struct HostCallGuard {
 };
 
 int run_host(int path, int ntiles, std::vector<HostSlot>& slots, const HcBox* tiles, const Consts& k, HcStats* stats, const EosOpts* eos = nullptr,
-             const GroupLauncher* custom = nullptr) {
+             const GroupLauncher* custom = nullptr, bool with_react = false) {
+    // with_react: the last three slots are the SAVE_REACT FABs (pure outputs), the ones before them the integrator's
     int dev; if (int rc = current_device(dev)) return rc;
     HostPipe* hp = nullptr;
     if (int rc = host_pipe(dev, hp)) return rc;
@@ -909,8 +1025,11 @@ int run_host(int path, int ntiles, std::vector<HostSlot>& slots, const HcBox* ti
         CUDA_TRY(cudaStreamWaitEvent(cs, e_in, 0));
         std::vector<const HcFab*> fabs(nf);
         for (int s = 0; s < nf; ++s) fabs[s] = dfab[s].data();
-        rc = custom ? (*custom)(n, fabs.data(), tiles + t0, cs)
-                    : launch(path, n, fabs.data(), nf, tiles + t0, k, nullptr, nullptr, cs, dstats, eos);
+        if (custom) rc = (*custom)(n, fabs.data(), tiles + t0, cs);
+        else if (with_react) {
+            const ReactFabs rf{fabs[nf - 3], fabs[nf - 2], fabs[nf - 1]};
+            rc = launch(path, n, fabs.data(), nf - 3, tiles + t0, k, nullptr, nullptr, cs, dstats, eos, &rf);
+        } else rc = launch(path, n, fabs.data(), nf, tiles + t0, k, nullptr, nullptr, cs, dstats, eos);
         if (rc != HC_OK) break;
         CUDA_TRY(cudaEventRecord(e_k, cs));
         if (cs == hp->comp2) e_last2 = e_k;
@@ -1129,6 +1248,24 @@ int hc_integrate_struct_batch(int ntiles, const HcFab* s_old, const HcFab* diag,
     return launch(PATH_STRUCT, ntiles, fabs, 6, tiles, k, stats, cell_stats, (cudaStream_t)stream);
 }
 
+int hc_integrate_struct_react_batch(int ntiles, const HcFab* s_old, const HcFab* diag, const HcFab* s_new, const HcFab* hydro_src,
+                                    const HcFab* reset_src, const HcFab* ir, const HcFab* react_in, const HcFab* react_out,
+                                    const HcFab* react_out_work, const HcBox* tiles, double a, double a_end, double dt, int sdc_iter,
+                                    const HcParams* prm, HcStats* stats, HcCellStat* cell_stats, void* stream) {
+    if (!valid_params(prm) || (ntiles > 0 && (!s_old || !diag || !s_new || !hydro_src || !reset_src || !ir || !react_in || !react_out || !react_out_work || !tiles)) ||
+        !(a > 0.0) || !(a_end > 0.0)) {
+        set_err("bad argument"); return HC_ERR_ARG;
+    }
+    // without sources the reference's ode_eos_save_react_arrays reads rhoe_src_vode / e_src_vode through null pointers (f_rhs_struct.H:197-198,251-252)
+    if (sdc_iter < 0) { set_err("the SAVE_REACT dumps need the SDC sources (sdc_iter >= 0)"); return HC_ERR_ARG; }
+    const auto rates_sp = rates_snapshot();
+    if (!rates_sp) { set_err("hc_tables_upload has not been called"); return HC_ERR_NO_TABLES; }
+    const Consts k = make_consts_struct(rates_sp->data(), *prm, a, a_end, dt, sdc_iter);
+    const HcFab* fabs[6] = {s_old, diag, s_new, hydro_src, reset_src, ir};
+    const ReactFabs rf{react_in, react_out, react_out_work};
+    return launch(PATH_STRUCT, ntiles, fabs, 6, tiles, k, stats, cell_stats, (cudaStream_t)stream, nullptr, nullptr, &rf);
+}
+
 int hc_integrate_struct(const HcFab* s_old, const HcFab* diag, const HcFab* s_new, const HcFab* hydro_src, const HcFab* reset_src,
                         const HcFab* ir, HcBox tile, double a, double a_end, double dt, int sdc_iter, const HcParams* prm,
                         HcStats* stats, HcCellStat* cell_stats, void* stream) {
@@ -1205,6 +1342,32 @@ int hc_integrate_struct_host(int ntiles, const HcFab* s_old, const HcFab* diag, 
         {reset_src, {0}, {}},
         {ir, {}, src ? std::vector<int>{0} : std::vector<int>{}}};   // pure output: only the tile's cells travel back (copy_tile_d2h), host ghost cells keep their values
     return run_host(PATH_STRUCT, ntiles, slots, tiles, k, stats);
+}
+
+int hc_integrate_struct_react_host(int ntiles, const HcFab* s_old, const HcFab* diag, const HcFab* s_new, const HcFab* hydro_src,
+                                   const HcFab* reset_src, const HcFab* ir, const HcFab* react_in, const HcFab* react_out,
+                                   const HcFab* react_out_work, const HcBox* tiles, double a, double a_end, double dt, int sdc_iter,
+                                   const HcParams* prm, HcStats* stats) {
+    if (ntiles <= 0 || !s_old || !diag || !s_new || !hydro_src || !reset_src || !ir || !react_in || !react_out || !react_out_work || !tiles ||
+        !valid_params(prm) || !(a > 0.0) || !(a_end > 0.0)) {
+        set_err("bad argument"); return HC_ERR_ARG;
+    }
+    if (sdc_iter < 0) { set_err("the SAVE_REACT dumps need the SDC sources (sdc_iter >= 0)"); return HC_ERR_ARG; }
+    const auto rates_sp = rates_snapshot();
+    if (!rates_sp) { set_err("hc_tables_upload has not been called"); return HC_ERR_NO_TABLES; }
+    if (stats) std::memset(stats, 0, sizeof *stats);
+    const Consts k = make_consts_struct(rates_sp->data(), *prm, a, a_end, dt, sdc_iter);
+    std::vector<HostSlot> slots = {
+        {s_old, {DENS, EINT}, {}},
+        {diag, prm->inhomo_reion ? std::vector<int>{TEMP, NE, ZHI} : std::vector<int>{TEMP, NE}, {TEMP, NE}},
+        {s_new, {DENS, EDEN, EINT}, {EDEN, EINT}},
+        {hydro_src, {DENS, EINT}, {}},
+        {reset_src, {0}, {}},
+        {ir, {}, {0}},
+        {react_in, {}, {0, 1, 2, 3, 4, 5, 6}},
+        {react_out, {}, {0, 1, 2, 3, 4, 5, 6}},
+        {react_out_work, {}, {0, 1, 2, 3, 4, 5, 6, 7, 8}}};
+    return run_host(PATH_STRUCT, ntiles, slots, tiles, k, stats, nullptr, nullptr, true);
 }
 
 int hc_compute_new_temp_host(int ntiles, const HcFab* state, const HcFab* diag, const HcBox* tiles, double a, const HcParams* prm,

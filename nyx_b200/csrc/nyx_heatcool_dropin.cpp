@@ -23,6 +23,9 @@
 // (sundials_reltol, use_typical_steps, ...) are therefore only read inside Nyx:: member functions.
 #include <AMReX_MultiFab.H>
 #include <AMReX_ParmParse.H>
+#ifdef SAVE_REACT
+#include <AMReX_PlotFileUtil.H>
+#endif
 #include <Nyx.H>
 #if __has_include(<atomic_rates_data.H>)
 #include <atomic_rates_data.H>   // the reference's AtomicRates image, filled by its own tabulate_rates (Nyx::heatcool_setup, unchanged)
@@ -198,12 +201,25 @@ int Nyx::integrate_state_vec_mfin(Array4<Real> const& state4, Array4<Real> const
 }
 
 namespace {
+// react (SAVE_REACT builds): the three diagnostic FAB lists react_in / react_out / react_out_work, or nullptr
 int struct_batch(std::vector<HcFab> f[6], std::vector<HcBox>& t, Real a, Real a_end, Real dt, int sdc_iter, const NyxFlags& fl, long int old_max,
-                 long int& new_max) {
+                 long int& new_max, std::vector<HcFab>* react = nullptr) {
     if (t.empty()) return 0;
     ensure_tables();
     const HcParams p = make_params(fl, old_max);
     HcStats st{};
+    if (react) {
+#ifdef AMREX_USE_GPU
+        const int rc = hc_integrate_struct_react_batch((int)t.size(), f[0].data(), f[1].data(), f[2].data(), f[3].data(), f[4].data(), f[5].data(),
+                                                       react[0].data(), react[1].data(), react[2].data(), t.data(), a, a_end, dt, sdc_iter, &p,
+                                                       want_stats(fl) ? &st : nullptr, nullptr, nyx_stream());
+#else
+        const int rc = hc_integrate_struct_react_host((int)t.size(), f[0].data(), f[1].data(), f[2].data(), f[3].data(), f[4].data(), f[5].data(),
+                                                      react[0].data(), react[1].data(), react[2].data(), t.data(), a, a_end, dt, sdc_iter, &p, &st);
+#endif
+        finish(st, fl.use_typical_steps, new_max);
+        return check(rc);
+    }
 #ifdef AMREX_USE_GPU
     const int rc = hc_integrate_struct_batch((int)t.size(), f[0].data(), f[1].data(), f[2].data(), f[3].data(), f[4].data(), f[5].data(),
                                              t.data(), a, a_end, dt, sdc_iter, &p, want_stats(fl) ? &st : nullptr, nullptr, nyx_stream());
@@ -312,24 +328,63 @@ int Nyx::integrate_state_struct(MultiFab& S_old, MultiFab& S_new, MultiFab& D_ol
     }
 #endif
     std::vector<HcFab> f[6]; std::vector<HcBox> t;
+#ifdef SAVE_REACT
+    // :126-135, the same three MultiFabs with the same component names
+    const amrex::Vector<std::string> react_in_names {"eptr-idx", "f_rhs_data-ptr-rho_init_vode-idx", "f_rhs_data-ptr-rhoe_src_vode-idx", "f_rhs_data-ptr-e_src_vode-idx", "abstol_ptr-idx", "f_rhs_data-ptr-a", "time_in"};
+    const amrex::Vector<std::string> react_out_names {"dptr-idx", "f_rhs_data-ptr-rho_vode-idx", "f_rhs_data-ptr-T_vode-idx", "f_rhs_data-ptr-ne_vode-idx", "abstol_achieve_ptr-idx", "a_end", "delta_time"};
+    const amrex::Vector<std::string> react_out_work_names {"nst", "netf", "nfe", "nni", "ncfn", "nsetups", "nje", "ncfl", "nfeLS"};
+    MultiFab react_in(grids, dmap, react_in_names.size(), NUM_GROW);
+    MultiFab react_out(grids, dmap, react_out_names.size(), NUM_GROW);
+    MultiFab react_out_work(grids, dmap, react_out_work_names.size(), NUM_GROW);
+    std::vector<HcFab> react[3];
+#endif
     for (MFIter mfi(S_old); mfi.isValid(); ++mfi) {
         // C-ABI order == integrate_state_struct_mfin's: state, diag, state_n, hydro_src, reset_src, IR
         f[0].push_back(to_fab(S_old.array(mfi))); f[1].push_back(to_fab(D_old.array(mfi))); f[2].push_back(to_fab(S_new.array(mfi)));
         f[3].push_back(to_fab(hydro_src.array(mfi))); f[4].push_back(to_fab(reset_src.array(mfi))); f[5].push_back(to_fab(IR.array(mfi)));
         t.push_back(to_box(mfi.validbox()));
+#ifdef SAVE_REACT
+        react[0].push_back(to_fab(react_in.array(mfi))); react[1].push_back(to_fab(react_out.array(mfi))); react[2].push_back(to_fab(react_out_work.array(mfi)));
+#endif
     }
+#ifdef SAVE_REACT
+    const int rc = struct_batch(f, t, a, a_end, delta_time, sdc_iter, NYX_HC_FLAGS(), store_steps, new_max_sundials_steps, react);
+    {   // :165-182
+#ifdef NO_HYDRO
+        Real cur_time = state[PhiGrav_Type].curTime();
+#else
+        Real cur_time = state[State_Type].curTime();
+#endif
+        auto plotfilename = Concatenate("plt_react_in", nStep(), 5);
+        WriteSingleLevelPlotfile(plotfilename, react_in, react_in_names, Geom(), cur_time, nStep());
+        plotfilename = Concatenate("plt_react_out", nStep(), 5);
+        WriteSingleLevelPlotfile(plotfilename, react_out, react_out_names, Geom(), cur_time, nStep());
+        plotfilename = Concatenate("plt_react_out_work", nStep(), 5);
+        WriteSingleLevelPlotfile(plotfilename, react_out_work, react_out_work_names, Geom(), cur_time, nStep());
+    }
+    return rc;
+#else
     return struct_batch(f, t, a, a_end, delta_time, sdc_iter, NYX_HC_FLAGS(), store_steps, new_max_sundials_steps);
+#endif
 }
 
 // HC/integrate_state_with_source_3d.cpp:187-709: one tile
 int Nyx::integrate_state_struct_mfin(Array4<Real> const& state4, Array4<Real> const& diag_eos4, Array4<Real> const& state_n4,
                                      Array4<Real> const& hydro_src4, Array4<Real> const& reset_src4, Array4<Real> const& IR4,
+#ifdef SAVE_REACT
+                                     Array4<Real> const& react_in_arr, Array4<Real> const& react_out_arr, Array4<Real> const& react_out_work_arr,
+#endif
                                      const Box& tbx, const Real& a, const Real& a_end, const Real& delta_time,
                                      long int& old_max_steps, long int& new_max_steps, const int sdc_iter)
 {
     std::vector<HcFab> f[6] = {{to_fab(state4)}, {to_fab(diag_eos4)}, {to_fab(state_n4)}, {to_fab(hydro_src4)}, {to_fab(reset_src4)}, {to_fab(IR4)}};
     std::vector<HcBox> t{to_box(tbx)};
+#ifdef SAVE_REACT
+    std::vector<HcFab> react[3] = {{to_fab(react_in_arr)}, {to_fab(react_out_arr)}, {to_fab(react_out_work_arr)}};
+    return struct_batch(f, t, a, a_end, delta_time, sdc_iter, NYX_HC_FLAGS(), old_max_steps, new_max_steps, react);
+#else
     return struct_batch(f, t, a, a_end, delta_time, sdc_iter, NYX_HC_FLAGS(), old_max_steps, new_max_steps);
+#endif
 }
 
 

@@ -885,7 +885,7 @@ static int cv_step(cvs* m) {
 /* CVodeCreate + CVodeInit + CVodeSVtolerances + CVDiag + CVodeSetMaxNumSteps [+SetMaxStep, SetConstraints] + CVode(CV_NORMAL)
  * for one component: SUN/cvode/cvode.c:255-548,716-775,990-1466,1490-1560; call sequence HC/integrate_state_vec_3d.cpp:251-284. */
 static int cvode_scalar(cellctx* c, double y0, double abstol, double reltol, double tout, long mxstep, double hmax_inv,
-                        int use_constraint, double* yout, hco_cellstats* st) {
+                        int use_constraint, double* yout, hco_cellstats* st, double* ele) {
     cvs mem; cvs* m = &mem;
     memset(m, 0, sizeof *m);
     m->c = c; m->uround = DBL_EPSILON; m->reltol = reltol; m->Vabstol = abstol; m->atolmin0 = (abstol == 0.0);
@@ -938,6 +938,7 @@ static int cvode_scalar(cellctx* c, double y0, double abstol, double reltol, dou
         }
     }
 done:
+    if (ele) *ele = m->acor;   /* CVodeGetEstLocalErrors: N_VScale(ONE, cv_acor, ele), SUN/cvode/cvode_io.c:1346-1360 */
     if (st) {
         st->nst = m->nst; st->netf = m->netf; st->nfe = m->nfe; st->nni = m->nni; st->ncfn = m->nnf; st->nsetups = m->nsetups;
         st->nfeLS = m->nfeDI; st->flag = istate; st->ne_iters = c->ne_iters; st->attempts = m->attempts;
@@ -965,7 +966,7 @@ int hco_integrate_state_vec(const hco_rates* r, const hco_params* p, const hco_f
         c.rpar[0] = *at(diag, i, j, k, TEMP); c.rpar[1] = *at(diag, i, j, k, NE); c.rpar[2] = rho; c.rpar[3] = 1 / a - 1;
         const double abstol = nv_scale(p->atol_factor, e0);   /* N_VScale(abstol,u,abstol_vec) :254 */
         double e_out;
-        cvode_scalar(&c, e0, abstol, p->rtol, dt, p->max_steps, hmax_inv, p->use_constraint, &e_out, stats ? &stats[idx] : NULL);
+        cvode_scalar(&c, e0, abstol, p->rtol, dt, p->max_steps, hmax_inv, p->use_constraint, &e_out, stats ? &stats[idx] : NULL, NULL);
         /* ode_eos_finalize */
         double T_vode = c.rpar[0], ne_vode = c.rpar[1];
         const double rho_vode = c.rpar[2], z_vode = c.rpar[3];
@@ -994,6 +995,16 @@ int hco_integrate_state_struct(const hco_rates* r, const hco_params* p, const hc
                                const hco_fab* diag, const hco_fab* hydro_src, const hco_fab* reset_src, const hco_fab* ir,
                                const int lo[3], const int hi[3], double a, double a_end, double dt, int sdc_iter,
                                hco_cellstats* stats) {
+    return hco_integrate_state_struct_react(r, p, s_old, s_new, diag, hydro_src, reset_src, ir, NULL, NULL, NULL, lo, hi, a, a_end, dt, sdc_iter, stats);
+}
+
+/* the SAVE_REACT build of the same function (HC/integrate_state_with_source_3d.cpp:126-183,602-631): react_in / react_out / react_out_work
+ * (7, 7, 9 components; all three NULL: the plain build) as ode_eos_save_react_arrays fills them (HC/f_rhs_struct.H:213-267) */
+int hco_integrate_state_struct_react(const hco_rates* r, const hco_params* p, const hco_fab* s_old, const hco_fab* s_new,
+                                     const hco_fab* diag, const hco_fab* hydro_src, const hco_fab* reset_src, const hco_fab* ir,
+                                     const hco_fab* react_in, const hco_fab* react_out, const hco_fab* react_out_work,
+                                     const int lo[3], const int hi[3], double a, double a_end, double dt, int sdc_iter,
+                                     hco_cellstats* stats) {
     /* ode_eos_setup :73-93 */
     int flash_h, flash_he;
     if (p->zhi_flash > 0.0) flash_h = (p->inhomo_reion > 0) ? 0 : 1; else flash_h = 0;
@@ -1025,8 +1036,11 @@ int hco_integrate_state_struct(const hco_rates* r, const hco_params* p, const hc
         double zhi = 0.0;
         if (p->inhomo_reion) { zhi = *at(diag, i, j, k, ZHI); c.JH = (z > zhi) ? 0 : 1; }
         const double abstol = nv_scale(p->atol_factor, e0);
-        double e_out;
-        cvode_scalar(&c, e0, abstol, p->rtol, dt, p->max_steps, hmax_inv, p->use_constraint, &e_out, stats ? &stats[idx] : NULL);
+        double e_out, ele = 0.0;
+        hco_cellstats st_cell; memset(&st_cell, 0, sizeof st_cell);
+        cvode_scalar(&c, e0, abstol, p->rtol, dt, p->max_steps, hmax_inv, p->use_constraint, &e_out, &st_cell, &ele);
+        if (stats) stats[idx] = st_cell;
+        const double e_cvode = e_out;   /* dptr[idx]: the finalize step works on a local copy (:283) */
 
         /* ode_eos_finalize_struct */
         const double e_orig = e0;
@@ -1089,6 +1103,30 @@ int hco_integrate_state_struct(const hco_rates* r, const hco_params* p, const hc
                 e_out = Tv / (p->gamma_minus_1 * MP_OVER_KB * mu);
             }
             eos_T_given_Re(r, p->gamma_minus_1, p->h_species, c.JH, c.JHe, &Tv, &nev, c.rho, e_out, a, sp);
+        }
+        if (react_in && react_out && react_out_work) {
+            /* ode_eos_save_react_arrays :241-266; T_vode / ne_vode are the values the finalize step left (its last EOS solve).  nje and ncfl
+             * are never assigned by GetFinalStats (HC/integrate_state_with_source_3d.cpp:792-810): uninitialised in the reference, 0 here.
+             * The counters are those of this cell's own CVODE instance (the reference: of the tile-wide instance, in every cell). */
+            *at(react_in, i, j, k, 0) = e0;
+            *at(react_out, i, j, k, 0) = e_cvode;
+            *at(react_in, i, j, k, 1) = c.rho_init;
+            *at(react_out, i, j, k, 1) = c.rho_init + dt * c.rho_src;
+            *at(react_in, i, j, k, 2) = c.rhoe_src;
+            *at(react_in, i, j, k, 3) = c.e_src;
+            *at(react_out, i, j, k, 2) = Tv;
+            *at(react_out, i, j, k, 3) = nev;
+            *at(react_in, i, j, k, 4) = abstol;
+            *at(react_out, i, j, k, 4) = ele;
+            *at(react_in, i, j, k, 5) = a;
+            *at(react_out, i, j, k, 5) = a_end;
+            *at(react_in, i, j, k, 6) = 0.0;
+            *at(react_out, i, j, k, 6) = dt;
+            *at(react_out_work, i, j, k, 0) = (double)st_cell.nst; *at(react_out_work, i, j, k, 1) = (double)st_cell.netf;
+            *at(react_out_work, i, j, k, 2) = (double)st_cell.nfe; *at(react_out_work, i, j, k, 3) = (double)st_cell.nni;
+            *at(react_out_work, i, j, k, 4) = (double)st_cell.ncfn; *at(react_out_work, i, j, k, 5) = (double)st_cell.nsetups;
+            *at(react_out_work, i, j, k, 6) = 0.0; *at(react_out_work, i, j, k, 7) = 0.0;
+            *at(react_out_work, i, j, k, 8) = (double)st_cell.nfeLS;
         }
         if (has_src) {
             *at(ir, i, j, k, 0) = IR;

@@ -204,6 +204,8 @@ class Port:
         fp = C.POINTER(HcoFab)
         ip = C.POINTER(C.c_int)
         lib.hco_integrate_state_vec.argtypes = [C.c_void_p, C.POINTER(HcoParams), fp, fp, ip, ip, C.c_double, C.c_double, C.c_void_p]
+        lib.hco_integrate_state_struct_react.argtypes = [C.c_void_p, C.POINTER(HcoParams)] + [fp] * 9 + [ip, ip, C.c_double, C.c_double, C.c_double,
+                                                                                                         C.c_int, C.c_void_p]
         lib.hco_integrate_state_struct.argtypes = [C.c_void_p, C.POINTER(HcoParams)] + [fp] * 6 + [ip, ip, C.c_double, C.c_double, C.c_double,
                                                                                                      C.c_int, C.c_void_p]
         lib.hco_eos_box.argtypes = [C.c_void_p, C.POINTER(HcoParams), fp, fp, ip, ip, C.c_double]
@@ -255,6 +257,18 @@ class Port:
         l, h = self._box(lo, hi)
         self.lib.hco_integrate_state_struct(self.rp, C.byref(p), *[C.byref(f) for f in fabs], l, h, a, a_end, dt, sdc_iter,
                                             st.ctypes.data_as(C.c_void_p) if want_stats else None)
+        return st
+
+    def integrate_state_struct_react(self, s_old, s_new, diag, hydro_src, reset_src, ir, react_in, react_out, react_out_work, lo, hi, a, a_end, dt,
+                                     sdc_iter=0, params=None):
+        """the SAVE_REACT build: integrate_state_struct + the three diagnostic FABs (7, 7, 9 components)"""
+        p = params or self.params()
+        fabs = [fab_of(x, lo) for x in (s_old, s_new, diag, hydro_src, reset_src, ir, react_in, react_out, react_out_work)]
+        n = (hi[0] - lo[0] + 1) * (hi[1] - lo[1] + 1) * (hi[2] - lo[2] + 1)
+        st = np.zeros((n, len(STAT_FIELDS)), dtype=np.int64)
+        l, h = self._box(lo, hi)
+        self.lib.hco_integrate_state_struct_react(self.rp, C.byref(p), *[C.byref(f) for f in fabs], l, h, a, a_end, dt, sdc_iter,
+                                                  st.ctypes.data_as(C.c_void_p))
         return st
 
     def compute_new_temp(self, state, diag, lo, hi, a, small_temp, large_temp, max_temp_dt, params=None):

@@ -23,6 +23,16 @@ LIBS="-L$WORK/sundials_inst/lib -lsundials_cvode -lsundials_nvecserial -lsundial
 /usr/bin/g++ -fopenmp -pthread -o "$OUT/Nyx3d.dropin.ex" $KEEP "$WORK/nyx_heatcool_dropin.o" $LIBS
 /usr/bin/g++ -fopenmp -pthread -o "$OUT/hctest_replay.dropin.ex" "$WORK/hctest_replay_ref.o" $(echo "$KEEP" | grep -v -e '/main.o' -e '/nyx_main.o') "$WORK/nyx_heatcool_dropin.o" $LIBS
 strip "$OUT/Nyx3d.dropin.ex" "$OUT/hctest_replay.dropin.ex"
+# SAVE_REACT flavour (needs the second reference build of tests/golden/make_react_fixture.sh): the drop-in compiled with -DSAVE_REACT against
+# the objects of the reference built with USE_SAVE_REACT=TRUE
+if [ -d "$WORK/LyA_react/tmp_build_dir/o/3d.gnu.TPROF.OMP.EXE" ]; then
+  OBJR="$WORK/LyA_react/tmp_build_dir/o/3d.gnu.TPROF.OMP.EXE"
+  CMDR=$(grep -- "-o Nyx3d" "$WORK/make_lya_react.log" | tail -1)
+  ( cd "$WORK/LyA_react" && ${CMDR%% -Xlinker*} -I"$ROOT/include" -c "$ROOT/nyx_b200/csrc/nyx_heatcool_dropin.cpp" -o "$WORK/nyx_heatcool_dropin_react.o" )
+  KEEPR=$(ls "$OBJR"/*.o | grep -v -e '/integrate_state_vec_3d.o' -e '/integrate_state_with_source_3d.o')
+  /usr/bin/g++ -fopenmp -pthread -o "$OUT/Nyx3d.dropin_react.ex" $KEEPR "$WORK/nyx_heatcool_dropin_react.o" $LIBS
+  strip "$OUT/Nyx3d.dropin_react.ex"
+fi
 # the reference's own executable beside them (oracle/_ref: built from the reference sources, test infrastructure)
 mkdir -p "$ROOT/oracle/_ref"
 cp "$(ls "$WORK"/LyA/Nyx3d.*.ex | head -1)" "$ROOT/oracle/_ref/Nyx3d.reference.ex"; strip "$ROOT/oracle/_ref/Nyx3d.reference.ex"

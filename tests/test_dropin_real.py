@@ -124,3 +124,36 @@ def test_hctest_hooks_of_the_dropin(tmp_path):
     assert np.abs(got["ir"][0][v] - ref["ir"][0][v]).max() < 1e-3 * np.abs(ref["ir"][0][v]).max()
     for comp in (0, 1, 2, 3):   # untouched components
         assert np.array_equal(got["s_new"][comp][v], ref["s_new"][comp][v])
+
+
+@pytest.mark.gpu
+def test_save_react_build_of_the_dropin(tmp_path):
+    """the drop-in compiled with -DSAVE_REACT against the objects of the reference built with USE_SAVE_REACT=TRUE (Exec/Make.Nyx:51-52): the first
+    Exec/LyA step writes plt_react_in / plt_react_out / plt_react_out_work like the reference's build of that step
+    (tests/golden/hctest_lya32/react_reference.json, from tests/golden/make_react_fixture.sh): components that depend on the inputs only and the
+    CVODE counters bit for bit, CVODE's solution and T to round-off of the device's libm"""
+    import hashlib
+    import json
+    exe = os.path.join(REAL, "Nyx3d.dropin_react.ex")
+    _need(exe)
+    _stage(tmp_path)
+    rc, out = _run(exe, ["inputs.rt", "max_step=1"] + QUIET, str(tmp_path), threads=1)
+    assert rc == 0, out[-2000:]
+    rr = json.load(open(os.path.join(FIX, "react_reference.json")))
+    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()   # noqa: E731
+    got = {nm: _plot(str(tmp_path / f"plt_react_{nm}00000")) for nm in ("in", "out", "out_work")}
+    for nm in got:
+        assert list(got[nm].keys()) == rr["names"][nm]
+    for c, n in enumerate(rr["names"]["in"]):
+        assert sha(got["in"][n]) == rr["sha256"]["in"][c], n
+    for c in (1, 3, 5, 6):
+        n = rr["names"]["out"][c]
+        assert sha(got["out"][n]) == rr["sha256"]["out"][c], n
+    for c in (0, 1, 2, 3, 4, 5, 7, 8):
+        n = rr["names"]["out_work"][c]
+        assert sha(got["out_work"][n]) == rr["sha256"]["out_work"][c], n
+    assert not got["out_work"]["nje"].any()
+    e, T = got["out"]["dptr-idx"], got["out"]["f_rhs_data-ptr-T_vode-idx"]
+    assert 2.1 < e.min() and e.max() < 2.2 and 208.0 < T.min() and T.max() < 213.0     # the reference's ranges for this step
+    e0 = got["in"]["eptr-idx"]
+    assert np.abs(e / e0 - 1).max() < 0.05

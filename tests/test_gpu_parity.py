@@ -201,6 +201,65 @@ def test_struct_matches_oracle(hc_lib, port, z, seed, src, flash):
     assert st.n_cells == n ** 3 and abs(st.n_failed - int((pst[:, 7] < 0).sum())) <= chaotic
 
 
+@pytest.mark.parametrize("z,seed,src,flash", [(3.0, 25, 0.05, "heii_now"), (5.99, 24, 0.05, "hi_now"), (6.0, 23, 0.2, "none")])
+def test_save_react_matches_oracle(hc_lib, port, z, seed, src, flash):
+    """the SAVE_REACT overload (Nyx.H:571-580; ode_eos_save_react_arrays f_rhs_struct.H:213-267) against the port's restatement of it -- itself
+    equal bit for bit to the reference built with USE_SAVE_REACT (tests/test_hctest_fixture.py) -- with sources, instantaneous reionization
+    heating (two EOS solves in the finalize step) and the +-20 % source stress case (floored cells)"""
+    torch = _torch()
+    n = 24
+    d = util.sdc_inputs(z, n, seed, src)
+    kw = util.FLASH_CASES[flash]
+    lo, hi = (0, 0, 0), (n - 1, n - 1, n - 1)
+    names = ("s_old", "diag", "s_new", "hydro_src", "reset_src", "ir")
+    dev = {k: torch.from_numpy(d[k]).cuda() for k in names}
+    rdev = [torch.zeros((c, n, n, n), dtype=torch.float64, device="cuda") for c in (7, 7, 9)]
+    csb = _cell_stats_buffer(n ** 3)
+    st = hc_lib.integrate_struct_react_batch(*[[capi.fab_of_torch(dev[k], lo)] for k in names], *[[capi.fab_of_torch(r, lo)] for r in rdev],
+                                             [capi.make_box(lo, hi)], d["a"], d["a_end"], d["dt"], 0, params=hc_lib.default_params(**kw),
+                                             cell_stats_ptr=csb.data_ptr())
+    torch.cuda.synchronize()
+    ref = {k: d[k].copy() for k in names}
+    ri, ro, rw = np.zeros((7, n, n, n)), np.zeros((7, n, n, n)), np.zeros((9, n, n, n))
+    pst = port.integrate_state_struct_react(ref["s_old"], ref["s_new"], ref["diag"], ref["hydro_src"], ref["reset_src"], ref["ir"], ri, ro, rw,
+                                            lo, hi, d["a"], d["a_end"], d["dt"], 0, params=port.params(**kw))
+    cs = _cs_to_numpy(csb)
+    chaotic = 4 if src >= 0.2 else 0
+    same = _compare_counts(cs, pst, f"react z={z} {flash}", chaotic_cells=chaotic).reshape(n, n, n)
+    gi, go, gw = (r.cpu().numpy() for r in rdev)
+    # functions of the inputs only: bit for bit
+    for c in range(7):
+        assert np.array_equal(gi[c], ri[c]), c
+    for c in (1, 5, 6):
+        assert np.array_equal(go[c], ro[c]), c
+    # the counters are the cell's own (those of cell_stats)
+    for c, f in ((0, "nst"), (1, "netf"), (2, "nfe"), (3, "nni"), (4, "ncfn"), (5, "nsetups"), (8, "nfe_ls")):
+        assert np.array_equal(gw[c].ravel(), cs[f].astype(np.float64)), f
+    assert not gw[6].any() and not gw[7].any()
+    m = same & ((pst[:, 7] == 0) & (cs["flag"] == 0)).reshape(n, n, n)
+    # CVODE's solution before the finalize step (may be negative / floored afterwards): in units of the integrator's own error weight
+    wgt = 1e-4 * np.abs(ro[0]) + ri[4]
+    # (stress case: the RAW solution of cells driven to e <= 0, which the finalize step floors afterwards: within the tolerance itself)
+    assert (np.abs(go[0] - ro[0]) / wgt)[m].max() < (1.0 if src >= 0.2 else 0.1)
+    # T, ne of the finalize step's LAST EOS solve (cells cooled below 100 K left out: the ne iteration stalls at its cap there, see above)
+    okT = m & (ro[2] > 1.0e2) & (np.abs(go[0] / ro[0] - 1) < 1e-7)
+    assert okT.mean() > 0.3
+    assert _rel(go[2], ro[2])[okT].max() < E_T_TIGHT and np.abs(go[3] - ro[3])[okT].max() < E_T_TIGHT
+    # the estimated local error is a cancellation residue (acor): same sign and size where it matters, i.e. where it is not round-off of the weight
+    big = m & (np.abs(ro[4]) > 1e-3 * wgt)
+    if big.any():
+        assert np.median(np.abs(go[4] / ro[4] - 1)[big]) < 1e-6
+    assert (np.abs(go[4] - ro[4]) / wgt)[m].max() < (1.0 if src >= 0.2 else 0.1)
+    # and the integration is the one of the plain entry point
+    dev2 = {k: torch.from_numpy(d[k]).cuda() for k in names}
+    st2 = hc_lib.integrate_struct_batch(*[[capi.fab_of_torch(dev2[k], lo)] for k in names], [capi.make_box(lo, hi)], d["a"], d["a_end"], d["dt"], 0,
+                                        params=hc_lib.default_params(**kw))
+    torch.cuda.synchronize()
+    assert st2.as_dict() == st.as_dict()
+    for k in ("s_new", "diag", "ir"):
+        assert torch.equal(dev[k], dev2[k]), k
+
+
 def test_grown_tiles_batch(hc_lib, port):
     """Two boxes with 4 ghost cells, tiles = grown boxes (integrate_state_grownvec, HC/integrate_state_vec_3d.cpp:367-396):
     ghost cells are integrated too, and state/diag FABs have different ghost widths."""

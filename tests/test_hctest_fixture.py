@@ -163,3 +163,106 @@ def test_gpu_replays_reference_snapshot(fx, hc_lib, port):
     mask = np.ones((34, 34, 34), dtype=bool); mask[1:33, 1:33, 1:33] = False
     assert got["s_new"][:, mask].tobytes() == fx["chunks"][0][0]["s_new"][:, mask].tobytes()
     assert got["ir"][:, mask].tobytes() == fx["chunks"][0][0]["ir"][:, mask].tobytes()
+
+
+# ---- SAVE_REACT (integrate_state_with_source_3d.cpp:126-183,602-631) -------------------------------------------------
+def _react_reference():
+    import json
+    return json.load(open(os.path.join(FIX, "react_reference.json")))
+
+
+def _sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def _port_react(fx, port, rr):
+    w, los = _replay_lists(fx)
+    lo, hi = fx["boxes"][0]
+    a, a_end, dt = float.fromhex(rr["a"]), float.fromhex(rr["a_end"]), float.fromhex(rr["dt"])   # the in-situ values (inputs.0 holds them rounded to 6 digits)
+    ri, ro, rw = np.zeros((7, 32, 32, 32)), np.zeros((7, 32, 32, 32)), np.zeros((9, 32, 32, 32))
+    order = ("s_old", "s_new", "diag", "hydro_src", "reset_src", "ir")
+    from oracle import pyref
+    import ctypes as C
+    p = port.params(h_species=float(fx["inputs"]["nyx.h_species"]))
+    fabs = [pyref.fab_of(w[k], los[k]) for k in order] + [pyref.fab_of(x, lo) for x in (ri, ro, rw)]
+    st = np.zeros((32 ** 3, len(pyref.STAT_FIELDS)), dtype=np.int64)
+    l, h = port._box(lo, hi)
+    port.lib.hco_integrate_state_struct_react(port.rp, C.byref(p), *[C.byref(f) for f in fabs], l, h, a, a_end, dt, 0, st.ctypes.data_as(C.c_void_p))
+    return dict(react_in=ri, react_out=ro, react_out_work=rw, stats=st, a=a, a_end=a_end, dt=dt)
+
+
+def test_port_save_react_equals_reference(fx, port):
+    """the SAVE_REACT dumps of the port equal, BIT FOR BIT, those the reference built with USE_SAVE_REACT=TRUE wrote for this step
+    (tests/golden/make_react_fixture.sh): all 7 + 7 components and the 7 assigned counters.  (In this smooth z = 100 field the tile-wide CVODE
+    instance and the per-cell one take the same 3 steps.)  nje is compared with 0: the reference never assigns it (its plotfile holds stack garbage)"""
+    rr = _react_reference()
+    pr = _port_react(fx, port, rr)
+    for c in range(7):
+        assert _sha(pr["react_in"][c]) == rr["sha256"]["in"][c], rr["names"]["in"][c]
+        assert _sha(pr["react_out"][c]) == rr["sha256"]["out"][c], rr["names"]["out"][c]
+    for c in (0, 1, 2, 3, 4, 5, 7, 8):
+        assert _sha(pr["react_out_work"][c]) == rr["sha256"]["out_work"][c], rr["names"]["out_work"][c]
+    assert rr["unique"]["out_work"][0] == [3.0] and rr["unique"]["out_work"][2] == [6.0] and rr["unique"]["out_work"][8] == [3.0]
+    assert not pr["react_out_work"][6].any()
+
+
+@pytest.mark.gpu
+def test_gpu_save_react_of_reference_snapshot(fx, hc_lib, port):
+    """the SAVE_REACT entry points (device-resident and host-buffer) on the reference's snapshot: inputs-only components and counters bit for bit
+    the reference's, CVODE's solution / T / the local error estimate against the port to round-off of the device's log10 / pow; the integration
+    itself is unchanged by the dumps"""
+    import torch
+    from nyx_b200 import capi
+    hc = hc_lib
+    rr = _react_reference()
+    pr = _port_react(fx, port, rr)
+    a, a_end, dt = pr["a"], pr["a_end"], pr["dt"]
+    lo, hi = fx["boxes"][0]
+    prm = hc.default_params(**hctest.params_from_inputs(fx["inputs"]))
+    w, los = _replay_lists(fx)
+    dev = {k: torch.from_numpy(w[k]).cuda() for k in hctest.FAB_ORDER}
+    rdev = {k: torch.full((n, 34, 34, 34), -7.0, dtype=torch.float64, device="cuda") for k, n in (("react_in", 7), ("react_out", 7), ("react_out_work", 9))}
+    fabs = [[capi.fab_of_torch(dev[k], los[k])] for k in ("s_old", "diag", "s_new", "hydro_src", "reset_src", "ir")]
+    rfabs = [[capi.fab_of_torch(rdev[k], (-1, -1, -1))] for k in ("react_in", "react_out", "react_out_work")]
+    st = hc.integrate_struct_react_batch(*fabs, *rfabs, [capi.make_box(lo, hi)], a, a_end, dt, 0, params=prm)
+    torch.cuda.synchronize()
+    assert st.n_cells == 32 ** 3 and st.n_failed == 0
+    got = {k: v.cpu().numpy() for k, v in rdev.items()}
+    inner = (slice(None), slice(1, 33), slice(1, 33), slice(1, 33))
+    for k in got:   # ghost cells of the react FABs are not written
+        mask = np.ones((34, 34, 34), dtype=bool); mask[1:33, 1:33, 1:33] = False
+        assert (got[k][:, mask] == -7.0).all()
+    gi, go, gw = got["react_in"][inner], got["react_out"][inner], got["react_out_work"][inner]
+    for c in range(7):
+        assert _sha(gi[c]) == rr["sha256"]["in"][c], rr["names"]["in"][c]
+    for c in (1, 3, 5, 6):
+        assert _sha(go[c]) == rr["sha256"]["out"][c], rr["names"]["out"][c]
+    for c in (0, 1, 2, 3, 4, 5, 7, 8):
+        assert _sha(gw[c]) == rr["sha256"]["out_work"][c], rr["names"]["out_work"][c]
+    assert not gw[6].any()
+    assert np.abs(go[0] / pr["react_out"][0] - 1).max() < 1e-9 and np.abs(go[2] / pr["react_out"][2] - 1).max() < 1e-9
+    # the local error estimate is a cancellation residue of size ~1e-13 x abstol here: compared in units of the tolerance
+    assert np.abs(go[4] - pr["react_out"][4]).max() < 1e-9 * gi[4].min()
+    # same integration as the plain entry point
+    w2, _ = _replay_lists(fx)
+    dev2 = {k: torch.from_numpy(w2[k]).cuda() for k in hctest.FAB_ORDER}
+    fabs2 = [[capi.fab_of_torch(dev2[k], los[k])] for k in ("s_old", "diag", "s_new", "hydro_src", "reset_src", "ir")]
+    st2 = hc.integrate_struct_batch(*fabs2, [capi.make_box(lo, hi)], a, a_end, dt, 0, params=prm)
+    torch.cuda.synchronize()
+    assert st2.as_dict() == st.as_dict()
+    for k in OUT_NAMES:
+        assert dev[k].cpu().numpy().tobytes() == dev2[k].cpu().numpy().tobytes(), k
+    # host-buffer entry point: same bits
+    wh, _ = _replay_lists(fx)
+    rh = {k: np.full((n, 34, 34, 34), -7.0) for k, n in (("react_in", 7), ("react_out", 7), ("react_out_work", 9))}
+    hl = [[capi.fab_of_numpy(wh[k], los[k])] for k in ("s_old", "diag", "s_new", "hydro_src", "reset_src", "ir")]
+    rl = [[capi.fab_of_numpy(rh[k], (-1, -1, -1))] for k in ("react_in", "react_out", "react_out_work")]
+    sth = hc.integrate_struct_react_host(*hl, *rl, [capi.make_box(lo, hi)], a, a_end, dt, 0, params=prm)
+    assert sth.as_dict() == st.as_dict()
+    for k in rh:
+        assert rh[k].tobytes() == got[k].tobytes(), k
+    for k in OUT_NAMES:
+        assert wh[k].tobytes() == dev[k].cpu().numpy().tobytes(), k
+    # without the SDC sources the reference's dump code reads null pointers: refused
+    with pytest.raises(Exception):
+        hc.integrate_struct_react_batch(*fabs, *rfabs, [capi.make_box(lo, hi)], a, a_end, dt, -1, params=prm)
