@@ -16,6 +16,9 @@
  *   hc_update_state_with_sources_batch     <- Nyx::update_state_with_sources (SDC) Source/TimeStep/Nyx_update_state_with_sources.cpp:9-121
  *   hc_enforce_minimum_density_batch       <- Nyx::enforce_minimum_density, floor   Source/TimeStep/Nyx_enforce_minimum_density.cpp:8-107,
  *                                             floor_density                         Source/TimeStep/Nyx_enforce_minimum_density.H:8-58
+ *   hc_enforce_min_density_cons_iter_batch <- Nyx::enforce_minimum_density_cons, one iteration    Nyx_enforce_minimum_density.cpp:190-236,
+ *   hc_finish_state_with_sources_batch        compute_mu_for_enforce_min / create_update_for_minimum  Nyx_enforce_minimum_density.H:60-200
+ *   hc_integrate_struct_react_batch        <- the SAVE_REACT overload of integrate_state_struct_mfin  Source/Driver/Nyx.H:571-580
  *   hc_fab_copy|add|subtract_batch         <- MultiFab::Copy / Add / Subtract around the call  Source/Hydro/sdc_hydro.cpp:83-84,94-95,112,135
  *   hc_init_zhi_batch                      <- Nyx::init_zhi, the cell loop            Source/Initialization/Nyx_initdata.cpp:163-213
  *   HcParams                               <- the nyx.* run-time flags of the path, Source/Driver/Nyx.cpp:116-181,
@@ -189,8 +192,9 @@ typedef struct HcSrcParams {
     double small_temp;        /* nyx.small_temp */
     double gamma_minus_1;     /* nyx.gamma - 1 */
     double h_species;         /* nyx.h_species */
-    int min_density_type;     /* nyx.enforce_min_density_type: "floor" (default) = HC_MIN_DENSITY_FLOOR.  "conservative" moves density between
-                                 neighbour cells through the host framework's FillPatch and is rejected with HC_ERR_ARG */
+    int min_density_type;     /* nyx.enforce_min_density_type: "floor" (default) = HC_MIN_DENSITY_FLOOR; "conservative" = HC_MIN_DENSITY_CONSERVATIVE moves
+                                 density between neighbour cells and needs the host framework's FillPatch between its iterations: the update then
+                                 runs as three calls (see hc_enforce_min_density_cons_iter_batch) */
     int sdc;                  /* 1: the reference's SDC build (enforce_minimum_density also resets hydro_src(rho)); 0: the non-SDC build */
 } HcSrcParams;
 void hc_default_src_params(HcSrcParams* p);
@@ -215,6 +219,28 @@ int hc_update_state_with_sources_host(int ntiles, const HcFab* s_old, const HcFa
                                       double* min_dens);
 int hc_enforce_minimum_density_host(int ntiles, const HcFab* s_old, const HcFab* s_new, const HcFab* ext_src_old, const HcFab* hydro_src,
                                     const HcFab* grav, const HcBox* tiles, double dt, double a_old, double a_new, const HcSrcParams* prm);
+/* nyx.enforce_min_density_type = "conservative" (Nyx::enforce_minimum_density_cons, Source/TimeStep/Nyx_enforce_minimum_density.cpp:101-330; per-cell
+ * functions compute_mu_for_enforce_min / create_update_for_minimum, Nyx_enforce_minimum_density.H:60-200).  With prm->min_density_type =
+ * HC_MIN_DENSITY_CONSERVATIVE the update runs as the reference's three sweeps, because the middle one exchanges ghost cells:
+ *   1. hc_update_state_with_sources_*            sweep (1) only: S_new = source update of S_old; *min_dens = minimum of the new density
+ *   2. while (the minimum over all ranks < small_dens and fewer than 10 iterations -- :179):
+ *          FillPatch(Sborder: the 6 state components of S_new with TWO filled ghost cells)          <- the caller (AMReX)
+ *          hc_enforce_min_density_cons_iter_*    ONE iteration (:190-236): S_new += div(mu grad Sborder) in the valid cells, reset_e_src =
+ *                                                the (rho e) part of it (SDC build); *min_dens_after = the new minimum of this rank.
+ *                                                A negative face coefficient (the reference aborts: "mu_x(i+1,j,k) < 0") returns HC_ERR_ARG
+ *      (still below small_dens after the loop: the reference aborts, "Not able to enforce small_dens this way after all" -- the caller's decision)
+ *   3. hc_finish_state_with_sources_*            sweep (3): gravity; density_enforced != 0 (step 2 ran) and prm->sdc: hydro_src(rho) = S_new(rho) - S_old(rho)
+ * reset_src may be NULL when prm->sdc == 0. */
+int hc_enforce_min_density_cons_iter_batch(int ntiles, const HcFab* sborder, const HcFab* s_new, const HcFab* reset_src, const HcBox* tiles,
+                                           const HcSrcParams* prm, double* min_dens_after, void* stream);
+int hc_enforce_min_density_cons_iter_host(int ntiles, const HcFab* sborder, const HcFab* s_new, const HcFab* reset_src, const HcBox* tiles,
+                                          const HcSrcParams* prm, double* min_dens_after);
+int hc_finish_state_with_sources_batch(int ntiles, const HcFab* s_old, const HcFab* s_new, const HcFab* ext_src_old, const HcFab* hydro_src,
+                                       const HcFab* grav, const HcBox* tiles, double dt, double a_old, double a_new, const HcSrcParams* prm,
+                                       int density_enforced, void* stream);
+int hc_finish_state_with_sources_host(int ntiles, const HcFab* s_old, const HcFab* s_new, const HcFab* ext_src_old, const HcFab* hydro_src,
+                                      const HcFab* grav, const HcBox* tiles, double dt, double a_old, double a_new, const HcSrcParams* prm,
+                                      int density_enforced);
 /* SURVEY 8f rank 4 -- Nyx::init_zhi, the cell loop (Source/Initialization/Nyx_initdata.cpp:198-209): diag(i,j,k,Zhi_comp = 2) =
  * zhi(i/ratio, j/ratio, k/ratio), zhi[t] = the one-component coarse reionization-redshift FAB that covers tile t coarsened by ratio
  * (the reference fills it with VisMF::Read + ParallelCopy; nyx_b200/nyxio.py reads the VisMF file) */

@@ -118,6 +118,10 @@ def declare(lib, prefix="hc_"):
     lib.hc_enforce_minimum_density_batch.argtypes = [C.c_int] + [fp] * 5 + [bp, C.c_double, C.c_double, C.c_double, qp, C.c_void_p]
     lib.hc_enforce_minimum_density_host.argtypes = [C.c_int] + [fp] * 5 + [bp, C.c_double, C.c_double, C.c_double, qp]
     lib.hc_update_state_with_sources_host.argtypes = [C.c_int] + [fp] * 5 + [bp, C.c_double, C.c_double, C.c_double, qp, _dp]
+    lib.hc_enforce_min_density_cons_iter_batch.argtypes = [C.c_int, fp, fp, fp, bp, qp, _dp, C.c_void_p]
+    lib.hc_enforce_min_density_cons_iter_host.argtypes = [C.c_int, fp, fp, fp, bp, qp, _dp]
+    lib.hc_finish_state_with_sources_batch.argtypes = [C.c_int] + [fp] * 5 + [bp, C.c_double, C.c_double, C.c_double, qp, C.c_int, C.c_void_p]
+    lib.hc_finish_state_with_sources_host.argtypes = [C.c_int] + [fp] * 5 + [bp, C.c_double, C.c_double, C.c_double, qp, C.c_int]
     for name in ("hc_fab_copy_batch", "hc_fab_add_batch", "hc_fab_subtract_batch"):
         getattr(lib, name).argtypes = [C.c_int, fp, C.c_int, fp, C.c_int, C.c_int, bp, C.c_void_p]
     lib.hc_init_zhi_batch.argtypes = [C.c_int, fp, fp, C.c_int, bp, C.c_void_p]
@@ -275,6 +279,27 @@ class NyxHC:
             self.check(self.lib.hc_enforce_minimum_density_host(len(tiles), *arrs, self._arr(tiles, HcBox), dt, a_old, a_new, C.byref(params)))
             return
         self.check(self.lib.hc_enforce_minimum_density_batch(len(tiles), *arrs, self._arr(tiles, HcBox), dt, a_old, a_new, C.byref(params), stream))
+
+    def enforce_min_density_cons_iter(self, sborder, s_new, reset_src, tiles, params, stream=None, host=False):
+        """one iteration of Nyx::enforce_minimum_density_cons on a border-filled copy of S_new (two ghost cells); returns the new minimum density"""
+        arrs = [self._arr(sborder, HcFab), self._arr(s_new, HcFab), self._arr(reset_src, HcFab) if reset_src is not None else None]
+        m = C.c_double(0.0)
+        if host:
+            self.check(self.lib.hc_enforce_min_density_cons_iter_host(len(tiles), *arrs, self._arr(tiles, HcBox), C.byref(params), C.byref(m)))
+        else:
+            self.check(self.lib.hc_enforce_min_density_cons_iter_batch(len(tiles), *arrs, self._arr(tiles, HcBox), C.byref(params), C.byref(m), stream))
+        return m.value
+
+    def finish_state_with_sources_batch(self, s_old, s_new, ext_src, hydro_src, grav, tiles, dt, a_old, a_new, params, density_enforced,
+                                        stream=None, host=False):
+        """sweep (3) of Nyx::update_state_with_sources after the conservative iterations"""
+        arrs = [self._arr(x, HcFab) for x in (s_old, s_new, ext_src, hydro_src, grav)]
+        if host:
+            self.check(self.lib.hc_finish_state_with_sources_host(len(tiles), *arrs, self._arr(tiles, HcBox), dt, a_old, a_new, C.byref(params),
+                                                                  int(density_enforced)))
+        else:
+            self.check(self.lib.hc_finish_state_with_sources_batch(len(tiles), *arrs, self._arr(tiles, HcBox), dt, a_old, a_new, C.byref(params),
+                                                                   int(density_enforced), stream))
 
     def fab_op_batch(self, op, dst, dcomp, src, scomp, ncomp, tiles, stream=None):
         """op in ("copy", "add", "subtract"): MultiFab::Copy / Add / Subtract of a component range over the tiles"""

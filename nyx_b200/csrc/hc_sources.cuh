@@ -25,6 +25,7 @@ struct SrcArgs {
     unsigned long long* min_key;   // ordered-integer image of the minimum new density (see dens_key)
     int use_flag;                  // <true> kernel: return at once unless *min_key decodes below small_dens
     int sdc;                       // SDC build of the reference: (2) resets hydro_src(rho)
+    int reset_hsrc;                // PHASE 2 only: the density was enforced (conservative variant) -> hydro_src(rho) = S_new(rho) - S_old(rho)
     double dt, a_old, a_half, a_half_inv, a_oldsq, a_newsq, a_new_inv, a_newsq_inv, dt_a_new, a_half_dt, dt_a_half;
     double small_dens, floor_rhoe; // floor_rhoe = small_dens * e(small_temp, Ne = 0)
 };
@@ -50,7 +51,11 @@ __host__ __device__ __forceinline__ double dens_from_key(unsigned long long k) {
 constexpr int SRC_THREADS = 256;
 constexpr int SRC_U = 2;            // cells per thread and pass: 42 loads in flight before the first store
 
-template <bool ENFORCE>
+// PHASE 0: sweeps (1) + (3) fused (the floor variant's path).  The "conservative" variant of enforce_minimum_density moves density between
+// neighbour cells of the sweep-(1) state through the caller's FillPatch, so there the two sweeps stay apart:
+// PHASE 1: sweep (1) only (+ the minimum);  PHASE 2: sweep (3) only, on the S_new the conservative iterations left (+ the SDC reset of
+// hydro_src(rho), Nyx_enforce_minimum_density.cpp:40-63, when a.reset_hsrc).
+template <bool ENFORCE, int PHASE = 0>
 __global__ void __launch_bounds__(SRC_THREADS) hc_sources_kernel(const __grid_constant__ SrcArgs a) {
     if (ENFORCE && a.use_flag) {
         if (!(dens_from_key(*a.min_key) < a.small_dens)) return;
@@ -82,16 +87,31 @@ __global__ void __launch_bounds__(SRC_THREADS) hc_sources_kernel(const __grid_co
                 const double* pg = Fg.p + fab_off(Fg, i, j, k);
                 ph[u] = Fh.p + fab_off(Fh, i, j, k);
                 po[u] = Fo.p + fab_off(Fo, i, j, k); nso[u] = Fo.nstride;
+                if (PHASE == 2) {
+                    // sweep (3) alone: the OLD state (rho, momenta), the gravity vector and the S_new of the sweeps before (kept in hs[])
 #pragma unroll
-                for (int n = 0; n < 6; ++n) { ui[u][n] = __ldg(pi + n * Fi.nstride); hs[u][n] = ph[u][n * Fh.nstride]; ex[u][n] = __ldg(pe + n * Fe.nstride); }
+                    for (int n = 0; n < 4; ++n) ui[u][n] = __ldg(pi + n * Fi.nstride);
 #pragma unroll
-                for (int n = 0; n < 3; ++n) g[u][n] = __ldg(pg + n * Fg.nstride);
+                    for (int n = 0; n < 6; ++n) hs[u][n] = po[u][n * nso[u]];
+                } else {
+#pragma unroll
+                    for (int n = 0; n < 6; ++n) { ui[u][n] = __ldg(pi + n * Fi.nstride); hs[u][n] = ph[u][n * Fh.nstride]; ex[u][n] = __ldg(pe + n * Fe.nstride); }
+                }
+                if (PHASE != 1) {
+#pragma unroll
+                    for (int n = 0; n < 3; ++n) g[u][n] = __ldg(pg + n * Fg.nstride);
+                }
             }
         }
 #pragma unroll
         for (int u = 0; u < SRC_U; ++u) {
             if (!on[u]) continue;
             double o[6];
+            if (PHASE == 2) {
+#pragma unroll
+                for (int n = 0; n < 6; ++n) o[n] = hs[u][n];
+                if (a.sdc && a.reset_hsrc) ph[u][0] = o[0] - ui[u][0];
+            } else {
             // sweep (1), Nyx_update_state_with_sources.cpp:47-73
             o[0] = ui[u][0] + hs[u][0] + a.dt * ex[u][0] * a.a_half_inv;
 #pragma unroll
@@ -104,7 +124,9 @@ __global__ void __launch_bounds__(SRC_THREADS) hc_sources_kernel(const __grid_co
                 o[n] = a.a_oldsq * ui[u][n] + hs[u][n] + a.a_half_dt * ex[u][n];
                 o[n] = o[n] * a.a_newsq_inv;
             }
-            if (!ENFORCE) {
+            }
+            if (PHASE == 2) {
+            } else if (!ENFORCE) {
                 if (o[0] < vmin) vmin = o[0];
             } else {
                 // sweep (2): floor_density, then (SDC) hydro_src(rho) = A_rho in every cell
@@ -115,6 +137,11 @@ __global__ void __launch_bounds__(SRC_THREADS) hc_sources_kernel(const __grid_co
                     o[4] = o[5];
                 }
                 if (a.sdc) ph[u][0] = o[0] - ui[u][0];
+            }
+            if (PHASE == 1) {
+#pragma unroll
+                for (int n = 0; n < 6; ++n) po[u][n * nso[u]] = o[n];
+                continue;
             }
             // sweep (3), :97-119 (rho and the momenta of the OLD state)
             const double rho = ui[u][0];
@@ -128,7 +155,7 @@ __global__ void __launch_bounds__(SRC_THREADS) hc_sources_kernel(const __grid_co
             for (int n = 0; n < 6; ++n) po[u][n * nso[u]] = o[n];
         }
     }
-    if (!ENFORCE) {
+    if (!ENFORCE && PHASE != 2) {
         // block minimum -> one atomicMin per CTA
 #pragma unroll
         for (int s = 16; s > 0; s >>= 1) { const double w = __shfl_xor_sync(0xffffffffu, vmin, s); if (w < vmin) vmin = w; }
@@ -142,6 +169,85 @@ __global__ void __launch_bounds__(SRC_THREADS) hc_sources_kernel(const __grid_co
             atomicMin(a.min_key, dens_key(m));
         }
     }
+}
+
+// ---- enforce_minimum_density, "conservative" variant: ONE iteration of the loop of Nyx::enforce_minimum_density_cons
+// (Source/TimeStep/Nyx_enforce_minimum_density.cpp:179-236) on a border-filled copy of the new state.  The reference does it in two sweeps
+// with three face-centred work arrays: compute_mu_for_enforce_min (Nyx_enforce_minimum_density.H:60-157) SCATTERS, from every cell below
+// small_dens of the tile grown by one, a diffusion coefficient to the faces it draws density through; create_update_for_minimum (:159-200)
+// then forms update(n) = div(mu grad state(n)) in the valid cells; then S_new += update, reset_e_src = update(rho e).  A face is written by at
+// most one of its two cells (a cell below small_dens < target = 1.01 small_dens has nothing to give), so the coefficient of a face is a pure
+// function of the densities within two cells of it: here every valid cell GATHERS its six coefficients and applies the update at once -- no
+// work arrays, no second sweep; same expressions, same order (-fmad=false).  FillPatch between iterations stays with the caller (it is the
+// host framework's ghost exchange); the new minimum density comes back for the caller's loop test.
+enum ConsSlot { CONS_SBORD = 0, CONS_SNEW = 1, CONS_RSRC = 2 };
+struct ConsArgs {
+    const TileDesc* tiles;
+    int ntiles;
+    long long ncells;
+    unsigned long long* min_key;   // minimum of the new density over the valid cells (dens_key image)
+    unsigned long long* n_bad;     // faces with a negative coefficient (the reference aborts: "mu_x(i+1,j,k) < 0")
+    double small_dens;
+    int sdc;                       // SDC build: reset_e_src = update(rho e)
+};
+__device__ __forceinline__ double cons_max0(double v) { return (v < 0.0) ? 0.0 : v; }   // amrex::max(v, 0.0)
+// the fraction of its neighbours' offers a cell below small_dens takes (:84-124); r points at the cell's density
+__device__ __forceinline__ double cons_fac(const double* r, long long js, long long ks, double target) {
+    const double total_need = target - r[0];
+    const double a_ihi = cons_max0((r[1] - target) / 6.0), a_ilo = cons_max0((r[-1] - target) / 6.0);
+    const double a_jhi = cons_max0((r[js] - target) / 6.0), a_jlo = cons_max0((r[-js] - target) / 6.0);
+    const double a_khi = cons_max0((r[ks] - target) / 6.0), a_klo = cons_max0((r[-ks] - target) / 6.0);
+    const double total_avail = a_ihi + a_ilo + a_jhi + a_jlo + a_khi + a_klo;
+    return (total_need < total_avail) ? total_need / total_avail : 1.0;
+}
+// coefficient of the face between the cell at r1 - st (lower) and the cell at r1 (upper) along the direction of stride st (:128-156)
+__device__ __forceinline__ double cons_mu(const double* r1, long long st, long long js, long long ks, double small, double target, unsigned& bad) {
+    const double lo = r1[-st], hi = r1[0];
+    double mu = 0.0;
+    if (lo < small) {          // the lower cell draws from its "hi" neighbour
+        const double from = cons_fac(r1 - st, js, ks, target) * cons_max0((hi - target) / 6.0);
+        if (from > 0) { mu = from / (hi - lo); if (mu < 0.) bad++; }
+    }
+    if (hi < small) {          // the upper cell draws from its "lo" neighbour
+        const double from = cons_fac(r1, js, ks, target) * cons_max0((lo - target) / 6.0);
+        if (from > 0) { mu = -from / (hi - lo); if (mu < 0.) bad++; }
+    }
+    return mu;
+}
+__global__ void __launch_bounds__(256) hc_min_dens_cons_kernel(const __grid_constant__ ConsArgs a) {
+    const double small = a.small_dens, target = 1.01 * a.small_dens;
+    double vmin = DBL_MAX;
+    unsigned bad = 0;
+    int ti = -1;
+    for (long long id = (long long)blockIdx.x * 256 + threadIdx.x; id < a.ncells; id += (long long)gridDim.x * 256) {
+        if (ti < 0) ti = find_tile_by_cell(a.tiles, a.ntiles, id);
+        while (ti + 1 < a.ntiles && a.tiles[ti + 1].offset <= id) ++ti;
+        const TileDesc& t = a.tiles[ti];
+        int i, j, k;
+        cell_of(t, id, i, j, k);
+        const HcFab& B = t.f[CONS_SBORD];
+        const HcFab& N = t.f[CONS_SNEW];
+        const long long js = B.jstride, ks = B.kstride;
+        const double* r = B.p + fab_off(B, i, j, k);   // component 0 = density
+        const double mx0 = cons_mu(r, 1, js, ks, small, target, bad), mx1 = cons_mu(r + 1, 1, js, ks, small, target, bad);
+        const double my0 = cons_mu(r, js, js, ks, small, target, bad), my1 = cons_mu(r + js, js, js, ks, small, target, bad);
+        const double mz0 = cons_mu(r, ks, js, ks, small, target, bad), mz1 = cons_mu(r + ks, ks, js, ks, small, target, bad);
+        double* pn = N.p + fab_off(N, i, j, k);
+#pragma unroll
+        for (int n = 0; n < 6; ++n) {
+            const double* s = r + (long long)n * B.nstride;
+            const double upd = mx1 * (s[1] - s[0]) - mx0 * (s[0] - s[-1]) + my1 * (s[js] - s[0]) - my0 * (s[0] - s[-js])
+                             + mz1 * (s[ks] - s[0]) - mz0 * (s[0] - s[-ks]);
+            const double v = pn[(long long)n * N.nstride] + upd;       // S_new.plus(update, 0, nComp, 0)
+            pn[(long long)n * N.nstride] = v;
+            if (n == 0 && v < vmin) vmin = v;
+            if (n == 5 && a.sdc) t.f[CONS_RSRC].p[fab_off(t.f[CONS_RSRC], i, j, k)] = upd;   // MultiFab::Copy(reset_e_src, update, Eint_comp, 0, 1, 0)
+        }
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) { const double w = __shfl_xor_sync(0xffffffffu, vmin, s); if (w < vmin) vmin = w; }
+    if ((threadIdx.x & 31) == 0) atomicMin(a.min_key, dens_key(vmin));
+    if (bad) atomicAdd(a.n_bad, (unsigned long long)bad);
 }
 
 // MultiFab::Copy / Add / Subtract of one component range (Source/Hydro/sdc_hydro.cpp:83-84,94-95,112,135): dst(dcomp + n) (=, +=, -=) src(scomp + n)

@@ -1115,6 +1115,7 @@ SrcArgs make_src_args(double dt, double a_old, double a_new, const HcSrcParams& 
 // mode 0: sweep (1)+(3) and the minimum, then the enforce kernel predicated on this call's own minimum (single rank);
 // mode 1: sweep (1)+(3) and the minimum accumulated into ext_min (device, caller-owned), no enforce kernel;
 // mode 2: the enforce kernel unconditionally (the caller has reduced the minimum over ranks / groups)
+// mode 3: ("conservative" variant) sweep (1) alone and the minimum;  mode 4 / 5: sweep (3) alone, 5 also resets hydro_src(rho) (SDC build)
 int launch_sources(int mode, int ntiles, const HcFab* const* fabs, const HcBox* tiles, double dt, double a_old, double a_new, const HcSrcParams& p,
                    double* min_dens_out, unsigned long long* ext_min, cudaStream_t stream) {
     int dev; if (int rc = current_device(dev)) return rc;
@@ -1129,11 +1130,15 @@ int launch_sources(int mode, int ntiles, const HcFab* const* fabs, const HcBox* 
     a.min_key = ext_min ? ext_min : reinterpret_cast<unsigned long long*>(scratch);
     const long long per_cta = SRC_THREADS * SRC_U;
     const int grid = stream_grid(ncells, per_cta, sms, 0);   // one pass per CTA: measured 1.19 / 2.25 ms against 1.22 / 2.48 ms with 8 CTAs per SM striding
-    if (mode != 2) hc_sources_kernel<false><<<grid, SRC_THREADS, 0, stream>>>(a);
-    if (mode == 0) { a.use_flag = 1; hc_sources_kernel<true><<<grid, SRC_THREADS, 0, stream>>>(a); }
-    if (mode == 2) { a.use_flag = 0; hc_sources_kernel<true><<<grid, SRC_THREADS, 0, stream>>>(a); }
+    if (mode == 3) hc_sources_kernel<false, 1><<<grid, SRC_THREADS, 0, stream>>>(a);                 // conservative variant: sweep (1) alone + minimum
+    else if (mode == 4 || mode == 5) { a.reset_hsrc = (mode == 5); hc_sources_kernel<false, 2><<<grid, SRC_THREADS, 0, stream>>>(a); }   // sweep (3) alone
+    else {
+        if (mode != 2) hc_sources_kernel<false><<<grid, SRC_THREADS, 0, stream>>>(a);
+        if (mode == 0) { a.use_flag = 1; hc_sources_kernel<true><<<grid, SRC_THREADS, 0, stream>>>(a); }
+        if (mode == 2) { a.use_flag = 0; hc_sources_kernel<true><<<grid, SRC_THREADS, 0, stream>>>(a); }
+    }
     CUDA_TRY(cudaGetLastError());
-    if (min_dens_out && mode != 2) {
+    if (min_dens_out && (mode == 0 || mode == 1 || mode == 3)) {
         unsigned long long key = 0;
         CUDA_TRY(cudaMemcpyAsync(&key, a.min_key, sizeof key, cudaMemcpyDeviceToHost, stream));
         CUDA_TRY(cudaStreamSynchronize(stream));
@@ -1403,9 +1408,8 @@ void hc_default_src_params(HcSrcParams* p) {
 #define HC_SRC_CHECK() \
     if (ntiles < 0 || (ntiles > 0 && (!s_old || !s_new || !ext_src_old || !hydro_src || !grav || !tiles)) || !valid_src_params(prm) || !(a_old > 0.0) || \
         !(a_new > 0.0)) { set_err("bad argument"); return HC_ERR_ARG; } \
-    if (prm->min_density_type != HC_MIN_DENSITY_FLOOR) { \
-        set_err("enforce_min_density_type = conservative exchanges density with neighbour cells through the host framework's FillPatch; only floor is on this path"); \
-        return HC_ERR_ARG; } \
+    if (prm->min_density_type != HC_MIN_DENSITY_FLOOR && prm->min_density_type != HC_MIN_DENSITY_CONSERVATIVE) { \
+        set_err("unknown min_density_type %d (Nyx: Don't know this enforce_min_density_type)", prm->min_density_type); return HC_ERR_ARG; } \
     if (int rc = check_src_fabs(ntiles, s_old, s_new, ext_src_old, hydro_src, grav)) return rc;
 
 int hc_update_state_with_sources_batch(int ntiles, const HcFab* s_old, const HcFab* s_new, const HcFab* ext_src_old, const HcFab* hydro_src,
@@ -1413,13 +1417,130 @@ int hc_update_state_with_sources_batch(int ntiles, const HcFab* s_old, const HcF
                                        double* min_dens, void* stream) {
     HC_SRC_CHECK();
     const HcFab* fabs[5] = {s_old, s_new, ext_src_old, hydro_src, grav};
-    return launch_sources(0, ntiles, fabs, tiles, dt, a_old, a_new, *prm, min_dens, nullptr, (cudaStream_t)stream);
+    // conservative variant: the source update alone; the caller iterates hc_enforce_min_density_cons_iter_* and ends with hc_finish_state_with_sources_*
+    const int mode = (prm->min_density_type == HC_MIN_DENSITY_CONSERVATIVE) ? 3 : 0;
+    return launch_sources(mode, ntiles, fabs, tiles, dt, a_old, a_new, *prm, min_dens, nullptr, (cudaStream_t)stream);
+}
+
+#define HC_FLOOR_ONLY() \
+    if (prm->min_density_type != HC_MIN_DENSITY_FLOOR) { \
+        set_err("the conservative variant is enforced by hc_enforce_min_density_cons_iter_* between the caller's FillPatch calls"); return HC_ERR_ARG; }
+
+namespace {
+int check_cons_fabs(int ntiles, const HcFab* sborder, const HcFab* s_new, const HcFab* reset_src, const HcBox* tiles, const HcSrcParams* prm) {
+    if (ntiles < 0 || (ntiles > 0 && (!sborder || !s_new || !tiles)) || !valid_src_params(prm)) { set_err("bad argument"); return HC_ERR_ARG; }
+    if (!(prm->small_dens > 0.0)) { set_err("the conservative variant needs small_dens > 0 (a cell below it must have nothing to give)"); return HC_ERR_ARG; }
+    if (prm->sdc && ntiles > 0 && !reset_src) { set_err("SDC build: reset_e_src is written by every iteration"); return HC_ERR_ARG; }
+    for (int t = 0; t < ntiles; ++t) {
+        if (tiles[t].hi[0] < tiles[t].lo[0] || tiles[t].hi[1] < tiles[t].lo[1] || tiles[t].hi[2] < tiles[t].lo[2]) continue;
+        if (!sborder[t].p || sborder[t].ncomp < 6 || !s_new[t].p || s_new[t].ncomp < 6 || (prm->sdc && (!reset_src[t].p || reset_src[t].ncomp < 1))) {
+            set_err("tile %d: Sborder and S_new need the 6 state components, reset_e_src one", t); return HC_ERR_ARG;
+        }
+        for (int d = 0; d < 3; ++d)
+            if (sborder[t].lo[d] > tiles[t].lo[d] - 2 || sborder[t].hi[d] < tiles[t].hi[d] + 2) {
+                set_err("tile %d: Sborder must hold two filled ghost cells around the tile (Nyx_enforce_minimum_density.cpp:116-118)", t); return HC_ERR_ARG;
+            }
+    }
+    return HC_OK;
+}
+
+// one iteration on device FABs; dmm (device, 16 bytes: [minimum key, initialised to all ones][bad faces, initialised to 0]) accumulates over calls
+int launch_cons_iter(int ntiles, const HcFab* const* fabs, const HcBox* tiles, const HcSrcParams& p, unsigned long long* dmm, cudaStream_t stream) {
+    int dev; if (int rc = current_device(dev)) return rc;
+    int sms = 0; if (int rc = sm_count_of(dev, sms)) return rc;
+    char* scratch; int n_used; long long ncells;
+    if (int rc = stage_tiles(ntiles, fabs, p.sdc ? 3 : 2, tiles, stream, scratch, n_used, ncells)) return rc;
+    if (ncells == 0) return HC_OK;
+    ConsArgs a{};
+    a.tiles = reinterpret_cast<const TileDesc*>(scratch + 256);
+    a.ntiles = n_used; a.ncells = ncells; a.min_key = dmm; a.n_bad = dmm + 1; a.small_dens = p.small_dens; a.sdc = p.sdc;
+    const int grid = (int)std::min<long long>((ncells + 255) / 256, (long long)sms * 8);
+    hc_min_dens_cons_kernel<<<grid, 256, 0, stream>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaFreeAsync(scratch, stream));
+    return HC_OK;
+}
+int finish_cons(unsigned long long* dmm, cudaStream_t stream, double* min_after) {
+    unsigned long long h[2] = {~0ull, 0ull};
+    CUDA_TRY(cudaMemcpyAsync(h, dmm, 16, cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    CUDA_TRY(cudaFreeAsync(dmm, stream));
+    if (min_after) *min_after = dens_from_key(h[0]);
+    if (h[1]) { set_err("enforce_minimum_density (conservative): %llu faces with a negative coefficient (the reference aborts: mu < 0)", h[1]); return HC_ERR_ARG; }
+    return HC_OK;
+}
+int new_cons_words(unsigned long long*& dmm, cudaStream_t stream) {
+    CUDA_TRY(cudaMallocAsync((void**)&dmm, 16, stream));
+    CUDA_TRY(cudaMemsetAsync(dmm, 0xff, 8, stream));
+    CUDA_TRY(cudaMemsetAsync(dmm + 1, 0, 8, stream));
+    return HC_OK;
+}
+}  // namespace
+
+int hc_enforce_min_density_cons_iter_batch(int ntiles, const HcFab* sborder, const HcFab* s_new, const HcFab* reset_src, const HcBox* tiles,
+                                           const HcSrcParams* prm, double* min_dens_after, void* stream_) {
+    if (int rc = check_cons_fabs(ntiles, sborder, s_new, reset_src, tiles, prm)) return rc;
+    if (min_dens_after) *min_dens_after = DBL_MAX;
+    if (ntiles == 0) return HC_OK;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    unsigned long long* dmm = nullptr;
+    if (int rc = new_cons_words(dmm, stream)) return rc;
+    const HcFab* fabs[3] = {sborder, s_new, reset_src};
+    if (int rc = launch_cons_iter(ntiles, fabs, tiles, *prm, dmm, stream)) return rc;
+    return finish_cons(dmm, stream, min_dens_after);
+}
+
+int hc_enforce_min_density_cons_iter_host(int ntiles, const HcFab* sborder, const HcFab* s_new, const HcFab* reset_src, const HcBox* tiles,
+                                          const HcSrcParams* prm, double* min_dens_after) {
+    if (int rc = check_cons_fabs(ntiles, sborder, s_new, reset_src, tiles, prm)) return rc;
+    if (min_dens_after) *min_dens_after = DBL_MAX;
+    if (ntiles == 0) return HC_OK;
+    int dev; if (int rc = current_device(dev)) return rc;
+    HostPipe* hp = nullptr;
+    if (int rc = host_pipe(dev, hp)) return rc;
+    unsigned long long* dmm = nullptr;
+    if (int rc = new_cons_words(dmm, hp->comp)) return rc;
+    const std::vector<int> all6 = {0, 1, 2, 3, 4, 5};
+    const HcSrcParams p = *prm;
+    std::vector<HostSlot> slots = {{sborder, all6, {}}, {s_new, all6, all6}};
+    if (p.sdc) slots.push_back({reset_src, {}, {0}});
+    GroupLauncher iter = [&](int n, const HcFab* const* fabs, const HcBox* tl, cudaStream_t st) { return launch_cons_iter(n, fabs, tl, p, dmm, st); };
+    const int rc = run_host(-1, ntiles, slots, tiles, Consts{}, nullptr, nullptr, &iter);
+    const int rc2 = finish_cons(dmm, hp->comp, min_dens_after);
+    return rc != HC_OK ? rc : rc2;
+}
+
+// sweep (3) of update_state_with_sources on the S_new the conservative iterations left; density_enforced: they ran (SDC build: hydro_src(rho) is reset)
+int hc_finish_state_with_sources_batch(int ntiles, const HcFab* s_old, const HcFab* s_new, const HcFab* ext_src_old, const HcFab* hydro_src,
+                                       const HcFab* grav, const HcBox* tiles, double dt, double a_old, double a_new, const HcSrcParams* prm,
+                                       int density_enforced, void* stream) {
+    HC_SRC_CHECK();
+    const HcFab* fabs[5] = {s_old, s_new, ext_src_old, hydro_src, grav};
+    return launch_sources(density_enforced ? 5 : 4, ntiles, fabs, tiles, dt, a_old, a_new, *prm, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+int hc_finish_state_with_sources_host(int ntiles, const HcFab* s_old, const HcFab* s_new, const HcFab* ext_src_old, const HcFab* hydro_src,
+                                      const HcFab* grav, const HcBox* tiles, double dt, double a_old, double a_new, const HcSrcParams* prm,
+                                      int density_enforced) {
+    HC_SRC_CHECK();
+    if (ntiles == 0) return HC_OK;
+    const std::vector<int> all6 = {0, 1, 2, 3, 4, 5};
+    const HcSrcParams p = *prm;
+    const bool reset = density_enforced && p.sdc;
+    std::vector<HostSlot> slots = {{s_old, {0, 1, 2, 3}, {}}, {s_new, all6, all6}, {ext_src_old, {}, {}},
+                                   {hydro_src, reset ? std::vector<int>{0} : std::vector<int>{}, reset ? std::vector<int>{0} : std::vector<int>{}},
+                                   {grav, {0, 1, 2}, {}}};
+    GroupLauncher fin = [&](int n, const HcFab* const* fabs, const HcBox* tl, cudaStream_t st) {
+        return launch_sources(density_enforced ? 5 : 4, n, fabs, tl, dt, a_old, a_new, p, nullptr, nullptr, st);
+    };
+    return run_host(-1, ntiles, slots, tiles, Consts{}, nullptr, nullptr, &fin);
 }
 
 int hc_enforce_minimum_density_batch(int ntiles, const HcFab* s_old, const HcFab* s_new, const HcFab* ext_src_old, const HcFab* hydro_src,
                                      const HcFab* grav, const HcBox* tiles, double dt, double a_old, double a_new, const HcSrcParams* prm,
                                      void* stream) {
     HC_SRC_CHECK();
+    HC_FLOOR_ONLY();
     const HcFab* fabs[5] = {s_old, s_new, ext_src_old, hydro_src, grav};
     return launch_sources(2, ntiles, fabs, tiles, dt, a_old, a_new, *prm, nullptr, nullptr, (cudaStream_t)stream);
 }
@@ -1427,6 +1548,7 @@ int hc_enforce_minimum_density_batch(int ntiles, const HcFab* s_old, const HcFab
 int hc_enforce_minimum_density_host(int ntiles, const HcFab* s_old, const HcFab* s_new, const HcFab* ext_src_old, const HcFab* hydro_src,
                                     const HcFab* grav, const HcBox* tiles, double dt, double a_old, double a_new, const HcSrcParams* prm) {
     HC_SRC_CHECK();
+    HC_FLOOR_ONLY();
     if (ntiles == 0) return HC_OK;
     // every cell again from the untouched inputs with the floor in between; hydro_src(rho) goes back as well
     // (S_new travels in too: whole components travel back, and its ghost cells must keep their values)
@@ -1458,7 +1580,7 @@ int hc_update_state_with_sources_host(int ntiles, const HcFab* s_old, const HcFa
     // (S_new travels in as well: whole components travel back, and its ghost cells must keep their values)
     const HcSrcParams p = *prm;
     GroupLauncher pass1 = [&](int n, const HcFab* const* fabs, const HcBox* tl, cudaStream_t st) {
-        return launch_sources(1, n, fabs, tl, dt, a_old, a_new, p, nullptr, dmin, st);
+        return launch_sources(p.min_density_type == HC_MIN_DENSITY_CONSERVATIVE ? 3 : 1, n, fabs, tl, dt, a_old, a_new, p, nullptr, dmin, st);
     };
     int rc = run_host(-1, ntiles, slots, tiles, Consts{}, nullptr, nullptr, &pass1);
     unsigned long long key = ~0ull;
@@ -1470,7 +1592,7 @@ int hc_update_state_with_sources_host(int ntiles, const HcFab* s_old, const HcFa
     if (rc != HC_OK) return rc;
     const double m = dens_from_key(key);
     if (min_dens) *min_dens = m;
-    if (m < p.small_dens)   // pass 2 (rare)
+    if (m < p.small_dens && p.min_density_type == HC_MIN_DENSITY_FLOOR)   // pass 2 (rare)
         rc = hc_enforce_minimum_density_host(ntiles, s_old, s_new, ext_src_old, hydro_src, grav, tiles, dt, a_old, a_new, prm);
     return rc;
 }

@@ -9,8 +9,11 @@
 // density floor and the gravity update of all local boxes in one fused streaming kernel.
 //
 // Differences a maintainer should know:
-//   * nyx.enforce_min_density_type = "floor" (the default, Source/Driver/Nyx.cpp:199) is on this path.  "conservative" exchanges density
-//     with neighbour cells through FillPatch and stays with the reference's translation unit: this file aborts on it;
+//   * nyx.enforce_min_density_type = "floor" (the default, Source/Driver/Nyx.cpp:199) takes the fused kernel.  "conservative"
+//     (Nyx::enforce_minimum_density_cons, Nyx_enforce_minimum_density.cpp:101-330) exchanges density with neighbour cells: the update then
+//     runs as the reference's three sweeps -- source update + minimum, at most 10 iterations of {FillPatch of a two-ghost-cell copy (AMReX,
+//     here), hc_enforce_min_density_cons_iter_batch}, gravity + the SDC reset of hydro_src(rho) -- with the reference's own loop test, prints
+//     and aborts;
 //   * the decision "is any new density below small_dens" is the reference's global S_new.min(): the local minimum comes back from the
 //     kernel, is reduced with ParallelDescriptor::ReduceRealMin, and a rank whose own boxes were fine but whose neighbours' were not
 //     runs the enforce kernel afterwards (it also rewrites hydro_src(rho) in every cell, as the reference does);
@@ -47,15 +50,16 @@ Nyx::update_state_with_sources( MultiFab& S_old, MultiFab& S_new,
                                 MultiFab& ext_src_old, MultiFab& hydro_source,
                                 MultiFab& grav_vector,
 #ifdef SDC
-                                MultiFab& /* reset_e_src: only the conservative variant writes it */,
+                                MultiFab& reset_e_src,   // only the conservative variant writes it
 #endif
                                 amrex::Real dt, amrex::Real a_old, amrex::Real a_new)
 {
     BL_PROFILE("Nyx::update_state_with_sources()");
     if (verbose)
       amrex::Print() << "Updating state with the hydro sources ... " << std::endl;
-    if (enforce_min_density_type != "floor")
-        amrex::Abort("nyx_hc: enforce_min_density_type = " + enforce_min_density_type + " is not on the B200 path (only floor); link the reference's Nyx_update_state_with_sources.cpp instead");
+    if (enforce_min_density_type != "floor" && enforce_min_density_type != "conservative")
+        amrex::Abort("Don't know this enforce_min_density_type");
+    const bool conservative = (enforce_min_density_type == "conservative");
 
     HcSrcParams p;
     hc_default_src_params(&p);
@@ -68,6 +72,7 @@ Nyx::update_state_with_sources( MultiFab& S_old, MultiFab& S_new,
 #else
     p.sdc = 0;
 #endif
+    p.min_density_type = conservative ? HC_MIN_DENSITY_CONSERVATIVE : HC_MIN_DENSITY_FLOOR;
 
     std::vector<HcFab> f[5]; std::vector<HcBox> t;
     for (MFIter mfi(S_new); mfi.isValid(); ++mfi) {
@@ -90,6 +95,56 @@ Nyx::update_state_with_sources( MultiFab& S_old, MultiFab& S_new,
     // S_new.min(Density_comp) of the reference is a reduction over all ranks (Nyx_enforce_minimum_density.cpp:22)
     Real global_min = local_min;
     ParallelDescriptor::ReduceRealMin(global_min);
+    if (conservative) {
+#if defined(NYX_HC_SHIM_BUILD)
+        amrex::Abort("nyx_hc: the conservative variant needs AMReX's FillPatch (not part of the test shim)");
+#else
+        // Nyx::enforce_minimum_density_cons (Nyx_enforce_minimum_density.cpp:101-330): the loop, its FillPatch and its aborts as in the reference;
+        // the two MFIter sweeps + S_new.plus + MultiFab::Copy of an iteration (:190-229) are one C-ABI call
+        const bool enforce = (global_min < small_dens);
+        if (enforce) {
+            const Real cur_time = state[State_Type].curTime();
+            MultiFab Sborder(grids, S_new.DistributionMap(), S_new.nComp(), 2);   // S_new has one ghost cell, two are needed (:116-118)
+            const Real rho_old_sum_before = S_old.sum(0), rho_new_sum_before = S_new.sum(0);
+            Real rho_new_min_after = global_min;
+            bool too_low = true;
+            int iter = 0;
+            while (too_low && iter < 10) {
+                FillPatch(*this, Sborder, 2, cur_time, State_Type, Density_comp, Sborder.nComp());
+                std::vector<HcFab> b, sn, rs;
+                for (MFIter mfi(S_new); mfi.isValid(); ++mfi) {
+                    b.push_back(src_fab(Sborder.array(mfi))); sn.push_back(src_fab(S_new.array(mfi)));
+#ifdef SDC
+                    rs.push_back(src_fab(reset_e_src.array(mfi)));
+#endif
+                }
+                Real local_after = std::numeric_limits<Real>::max();
+#ifdef AMREX_USE_GPU
+                src_check(hc_enforce_min_density_cons_iter_batch(n, b.data(), sn.data(), rs.empty() ? nullptr : rs.data(), t.data(), &p, &local_after, nullptr));
+#else
+                src_check(hc_enforce_min_density_cons_iter_host(n, b.data(), sn.data(), rs.empty() ? nullptr : rs.data(), t.data(), &p, &local_after));
+#endif
+                ParallelDescriptor::ReduceRealMin(local_after);
+                rho_new_min_after = local_after;
+                too_low = (rho_new_min_after < small_dens);
+                iter++;
+            }
+            const Real rho_new_sum_after = S_new.sum(0);
+            amrex::Print() << "After " << iter << " iterations " << std::endl;
+            amrex::Print() << "  SUM OF rho_old / rho_new / new rho_new " << rho_old_sum_before << " " << rho_new_sum_before << " " << rho_new_sum_after << std::endl;
+            if (rho_new_min_after < small_dens) amrex::Abort("Not able to enforce small_dens this way after all");
+        }
+#ifdef AMREX_USE_GPU
+        src_check(hc_finish_state_with_sources_batch(n, f[0].data(), f[1].data(), f[2].data(), f[3].data(), f[4].data(), t.data(), dt, a_old, a_new, &p,
+                                                     enforce ? 1 : 0, nullptr));
+        src_check(hc_sync(nullptr));
+#else
+        src_check(hc_finish_state_with_sources_host(n, f[0].data(), f[1].data(), f[2].data(), f[3].data(), f[4].data(), t.data(), dt, a_old, a_new, &p,
+                                                    enforce ? 1 : 0));
+#endif
+        return;
+#endif
+    }
     if (global_min < small_dens && !(local_min < small_dens) && n > 0) {
 #ifdef AMREX_USE_GPU
         src_check(hc_enforce_minimum_density_batch(n, f[0].data(), f[1].data(), f[2].data(), f[3].data(), f[4].data(), t.data(), dt, a_old, a_new, &p,

@@ -1289,6 +1289,65 @@ int hco_sources_finish_box(const hco_params* p, const hco_fab* uin, const hco_fa
 }
 
 /* the cell loop of Nyx::init_zhi (Source/Initialization/Nyx_initdata.cpp:198-209) over one box */
+/* One iteration of Nyx::enforce_minimum_density_cons (TS/Nyx_enforce_minimum_density.cpp:179-236) on one box: sbord = the new state with TWO
+ * filled ghost cells (the caller's FillPatch, :183), uout = S_new, rs = reset_e_src.  compute_mu_for_enforce_min on the box grown by one
+ * (TS/Nyx_enforce_minimum_density.H:60-157), create_update_for_minimum on the box (:159-200), S_new += update (:226), reset_e_src = update(Eint)
+ * (:229, SDC build).  Returns the new minimum density of the box; *bad counts the faces where the reference aborts ("mu < 0"). */
+double hco_enforce_min_cons_iter_box(const hco_fab* sbord, const hco_fab* uout, const hco_fab* rs, const int lo[3], const int hi[3],
+                                     double small_value, int sdc, long* bad) {
+    const int nx = hi[0] - lo[0] + 5, ny = hi[1] - lo[1] + 5, nz = hi[2] - lo[2] + 5;   /* the box grown by two holds every face index touched */
+    const size_t npts = (size_t)nx * ny * nz;
+    double* mu = (double*)calloc(3 * npts, sizeof(double));   /* mu_x.setVal(0.) ... (:186-188) */
+#define MU(d, i, j, k) mu[(size_t)(d) * npts + (size_t)((i) - lo[0] + 2) + (size_t)nx * ((size_t)((j) - lo[1] + 2) + (size_t)ny * (size_t)((k) - lo[2] + 2))]
+#define ST(i, j, k) (*at(sbord, i, j, k, DENS))
+    const double target = 1.01 * small_value;
+    long nbad = 0;
+    for (int k = lo[2] - 1; k <= hi[2] + 1; ++k) for (int j = lo[1] - 1; j <= hi[1] + 1; ++j) for (int i = lo[0] - 1; i <= hi[0] + 1; ++i) {
+        if (ST(i, j, k) < small_value) {
+            const double total_need = target - ST(i, j, k);
+            const double avail_from_ihi = dmax((ST(i + 1, j, k) - target) / 6.0, 0.0);
+            const double avail_from_ilo = dmax((ST(i - 1, j, k) - target) / 6.0, 0.0);
+            const double avail_from_jhi = dmax((ST(i, j + 1, k) - target) / 6.0, 0.0);
+            const double avail_from_jlo = dmax((ST(i, j - 1, k) - target) / 6.0, 0.0);
+            const double avail_from_khi = dmax((ST(i, j, k + 1) - target) / 6.0, 0.0);
+            const double avail_from_klo = dmax((ST(i, j, k - 1) - target) / 6.0, 0.0);
+            const double total_avail = avail_from_ihi + avail_from_ilo + avail_from_jhi + avail_from_jlo + avail_from_khi + avail_from_klo;
+            double fac;
+            if (total_need < total_avail) fac = total_need / total_avail; else fac = 1.0;
+            const double from_ihi = fac * avail_from_ihi, from_ilo = fac * avail_from_ilo;
+            const double from_jhi = fac * avail_from_jhi, from_jlo = fac * avail_from_jlo;
+            const double from_khi = fac * avail_from_khi, from_klo = fac * avail_from_klo;
+            if (from_ihi > 0) { MU(0, i + 1, j, k) = from_ihi / (ST(i + 1, j, k) - ST(i, j, k)); if (MU(0, i + 1, j, k) < 0.) nbad++; }
+            if (from_ilo > 0) { MU(0, i, j, k) = -from_ilo / (ST(i, j, k) - ST(i - 1, j, k)); if (MU(0, i, j, k) < 0.) nbad++; }
+            if (from_jhi > 0) { MU(1, i, j + 1, k) = from_jhi / (ST(i, j + 1, k) - ST(i, j, k)); if (MU(1, i, j + 1, k) < 0.) nbad++; }
+            if (from_jlo > 0) { MU(1, i, j, k) = -from_jlo / (ST(i, j, k) - ST(i, j - 1, k)); if (MU(1, i, j, k) < 0.) nbad++; }
+            if (from_khi > 0) { MU(2, i, j, k + 1) = from_khi / (ST(i, j, k + 1) - ST(i, j, k)); if (MU(2, i, j, k + 1) < 0.) nbad++; }
+            if (from_klo > 0) { MU(2, i, j, k) = -from_klo / (ST(i, j, k) - ST(i, j, k - 1)); if (MU(2, i, j, k) < 0.) nbad++; }
+        }
+    }
+    double m = DBL_MAX;
+    for (int k = lo[2]; k <= hi[2]; ++k) for (int j = lo[1]; j <= hi[1]; ++j) for (int i = lo[0]; i <= hi[0]; ++i) {
+        for (int n = 0; n < 6; ++n) {
+#define S(i, j, k) (*at(sbord, i, j, k, n))
+            const double update = MU(0, i + 1, j, k) * (S(i + 1, j, k) - S(i, j, k))
+                                 - MU(0, i, j, k) * (S(i, j, k) - S(i - 1, j, k))
+                                 + MU(1, i, j + 1, k) * (S(i, j + 1, k) - S(i, j, k))
+                                 - MU(1, i, j, k) * (S(i, j, k) - S(i, j - 1, k))
+                                 + MU(2, i, j, k + 1) * (S(i, j, k + 1) - S(i, j, k))
+                                 - MU(2, i, j, k) * (S(i, j, k) - S(i, j, k - 1));
+#undef S
+            *at(uout, i, j, k, n) += update;
+            if (n == EINT && sdc) *at(rs, i, j, k, 0) = update;
+        }
+        if (*at(uout, i, j, k, DENS) < m) m = *at(uout, i, j, k, DENS);
+    }
+#undef MU
+#undef ST
+    free(mu);
+    if (bad) *bad = nbad;
+    return m;
+}
+
 int hco_init_zhi_box(const hco_fab* diag, const hco_fab* zhi, const int lo[3], const int hi[3], int ratio) {
     for (int k = lo[2]; k <= hi[2]; ++k) for (int j = lo[1]; j <= hi[1]; ++j) for (int i = lo[0]; i <= hi[0]; ++i)
         *at(diag, i, j, k, ZHI) = *at(zhi, i / ratio, j / ratio, k / ratio, 0);

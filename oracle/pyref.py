@@ -136,6 +136,14 @@ class Reference:
         self.lib.nyxref_update_state_with_sources(len(b), bp, ngarr, _ptrs(s_old), _ptrs(s_new), _ptrs(ext_src), _ptrs(hydro_src), _ptrs(grav),
                                                   _ptrs(reset_src), dt, a_old, a_new, small_dens, small_temp)
 
+    def enforce_min_cons_iter(self, sborder, s_new, reset_src, lo, hi, small_dens, ng_new=0, ng_rs=0, sdc=1):
+        """one iteration of Nyx::enforce_minimum_density_cons on one box through the reference's own per-cell functions (ref_driver.cpp)"""
+        box = (C.c_int * 6)(*lo, *hi)
+        self.lib.nyxref_enforce_min_cons_iter.restype = C.c_double
+        self.lib.nyxref_enforce_min_cons_iter.argtypes = [C.POINTER(C.c_int), C.c_int, C.c_int, _dp, _dp, _dp, C.c_double, C.c_int]
+        return self.lib.nyxref_enforce_min_cons_iter(box, ng_new, ng_rs, sborder.ctypes.data_as(_dp), s_new.ctypes.data_as(_dp),
+                                                     reset_src.ctypes.data_as(_dp), small_dens, sdc)
+
     def ion_n(self, JH, JHe, U, nh, ne, gm1, hsp, z):
         out = np.zeros(4)
         self.lib.nyxref_ion_n(JH, JHe, U, nh, ne, gm1, hsp, z, out.ctypes.data_as(_dp))
@@ -310,6 +318,18 @@ class Port:
             lib.hco_sources_finish_box(C.byref(p), C.byref(f[0]), C.byref(f[1]), C.byref(f[3]), C.byref(f[4]), lo, hi, dt, a_old, a_new,
                                        small_dens, small_temp, int(decide < small_dens), sdc)
         return m
+
+    def enforce_min_cons_iter(self, sborder, s_new, reset_src, lo, hi, small_dens, ng_new=0, ng_rs=0, sdc=1):
+        """one iteration of Nyx::enforce_minimum_density_cons on one box; sborder covers the box grown by 2 (filled), s_new / reset_src the box
+        grown by ng_new / ng_rs.  Returns (new minimum density, faces with a negative coefficient)"""
+        l3 = C.c_int * 3
+        fp = C.POINTER(HcoFab)
+        self.lib.hco_enforce_min_cons_iter_box.restype = C.c_double
+        self.lib.hco_enforce_min_cons_iter_box.argtypes = [fp, fp, fp, l3, l3, C.c_double, C.c_int, C.POINTER(C.c_long)]
+        bad = C.c_long(0)
+        m = self.lib.hco_enforce_min_cons_iter_box(C.byref(fab_of(sborder, tuple(x - 2 for x in lo))), C.byref(fab_of(s_new, tuple(x - ng_new for x in lo))),
+                                                   C.byref(fab_of(reset_src, tuple(x - ng_rs for x in lo))), l3(*lo), l3(*hi), small_dens, sdc, C.byref(bad))
+        return m, bad.value
 
     def init_zhi(self, diag, diag_lo, zhi, zhi_lo, lo, hi, ratio):
         l3 = C.c_int * 3

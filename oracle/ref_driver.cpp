@@ -303,6 +303,36 @@ void Nyx::enforce_minimum_density_floor(MultiFab& S_new, Real a_new_in) {
     }
 }
 
+// One iteration of Nyx::enforce_minimum_density_cons (Nyx_enforce_minimum_density.cpp:179-236) on ONE box: the loop body RESTATED around the
+// reference's own per-cell functions compute_mu_for_enforce_min / create_update_for_minimum (Nyx_enforce_minimum_density.H:60-200, included
+// above); FillPatch -- AMReX's ghost exchange, not built here -- is the caller's: sborder arrives with its two ghost cells filled.
+extern "C" double nyxref_enforce_min_cons_iter(const int* box, int ng_new, int ng_rs, double* sborder, double* s_new, double* reset_src,
+                                               double small_dens, int sdc) {
+    const Box vbx(IntVect(box[0], box[1], box[2]), IntVect(box[3], box[4], box[5]));
+    FArrayBox Sb(amrex::grow(vbx, 2), 6, sborder), Sn(amrex::grow(vbx, ng_new), 6, s_new), Rs(amrex::grow(vbx, ng_rs), 1, reset_src);
+    // face-based coefficients with one ghost face (:122-124): stored on the cell box grown by two, which holds every face index touched
+    FArrayBox mux(amrex::grow(vbx, 2), 1), muy(amrex::grow(vbx, 2), 1), muz(amrex::grow(vbx, 2), 1), upd(vbx, 6);
+    mux.setVal(0.); muy.setVal(0.); muz.setVal(0.); upd.setVal(0.);
+    auto const& sbord = Sb.array();
+    auto const& mu_x_arr = mux.array(); auto const& mu_y_arr = muy.array(); auto const& mu_z_arr = muz.array();
+    auto const& upd_arr = upd.array();
+    const Real lsmall_dens = small_dens;
+    amrex::ParallelFor(amrex::grow(vbx, 1), [=](int i, int j, int k) noexcept {
+        compute_mu_for_enforce_min(i, j, k, Density_comp, sbord, mu_x_arr, mu_y_arr, mu_z_arr, lsmall_dens);
+    });
+    amrex::ParallelFor(vbx, [=](int i, int j, int k) noexcept {
+        create_update_for_minimum(i, j, k, sbord, mu_x_arr, mu_y_arr, mu_z_arr, upd_arr);
+    });
+    auto const& sn = Sn.array(); auto const& rs = Rs.array();
+    double mn = std::numeric_limits<double>::max();
+    amrex::ParallelFor(vbx, [&](int i, int j, int k) noexcept {
+        for (int n = 0; n < 6; ++n) sn(i, j, k, n) += upd_arr(i, j, k, n);       // S_new.plus(update, 0, nComp, 0)
+        if (sdc) rs(i, j, k, 0) = upd_arr(i, j, k, Eint_comp);                    // MultiFab::Copy(reset_e_src, update, Eint_comp, 0, 1, 0)
+        if (sn(i, j, k, Density_comp) < mn) mn = sn(i, j, k, Density_comp);
+    });
+    return mn;
+}
+
 extern "C" {
 // ng[6] / pointers in the reference's argument order: S_old, S_new, ext_src_old, hydro_source, grav_vector, reset_e_src
 // (6, 6, 6, 6, 3, 1 components)

@@ -17,10 +17,15 @@ OUT="$HERE/_build/real"; mkdir -p "$OUT"
 CMD=$(grep -- "-o Nyx3d" "$WORK/make_lya.log" | tail -1)
 CXXFLAGS="${CMD%% -Xlinker*}"
 ( cd "$WORK/LyA" && $CXXFLAGS -I"$ROOT/include" -c "$ROOT/nyx_b200/csrc/nyx_heatcool_dropin.cpp" -o "$WORK/nyx_heatcool_dropin.o" )
+# Nyx::update_state_with_sources (floor and conservative enforce_minimum_density) in place of the reference's translation unit
+( cd "$WORK/LyA" && $CXXFLAGS -I"$ROOT/include" -c "$ROOT/nyx_b200/csrc/nyx_sources_dropin.cpp" -o "$WORK/nyx_sources_dropin.o" )
 [ -f "$WORK/hctest_replay_ref.o" ] || ( cd "$WORK/LyA" && $CXXFLAGS -c "$HERE/golden/hctest_replay_ref.cpp" -o "$WORK/hctest_replay_ref.o" )
 KEEP=$(ls "$OBJ"/*.o | grep -v -e '/integrate_state_vec_3d.o' -e '/integrate_state_with_source_3d.o')
 LIBS="-L$WORK/sundials_inst/lib -lsundials_cvode -lsundials_nvecserial -lsundials_nvecopenmp -L$ROOT/nyx_b200/csrc -lnyx_hc -Wl,-rpath,/root/repo/nyx_b200/csrc -Wl,-rpath,$ROOT/nyx_b200/csrc"
 /usr/bin/g++ -fopenmp -pthread -o "$OUT/Nyx3d.dropin.ex" $KEEP "$WORK/nyx_heatcool_dropin.o" $LIBS
+#   Nyx3d.dropin_src.ex      the same, and Nyx_update_state_with_sources.o REPLACED by nyx_sources_dropin.o as well
+/usr/bin/g++ -fopenmp -pthread -o "$OUT/Nyx3d.dropin_src.ex" $(echo "$KEEP" | grep -v '/Nyx_update_state_with_sources.o') "$WORK/nyx_heatcool_dropin.o" "$WORK/nyx_sources_dropin.o" $LIBS
+strip "$OUT/Nyx3d.dropin_src.ex"
 /usr/bin/g++ -fopenmp -pthread -o "$OUT/hctest_replay.dropin.ex" "$WORK/hctest_replay_ref.o" $(echo "$KEEP" | grep -v -e '/main.o' -e '/nyx_main.o') "$WORK/nyx_heatcool_dropin.o" $LIBS
 strip "$OUT/Nyx3d.dropin.ex" "$OUT/hctest_replay.dropin.ex"
 # SAVE_REACT flavour (needs the second reference build of tests/golden/make_react_fixture.sh): the drop-in compiled with -DSAVE_REACT against

@@ -157,3 +157,36 @@ def test_save_react_build_of_the_dropin(tmp_path):
     assert 2.1 < e.min() and e.max() < 2.2 and 208.0 < T.min() and T.max() < 213.0     # the reference's ranges for this step
     e0 = got["in"]["eptr-idx"]
     assert np.abs(e / e0 - 1).max() < 0.05
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["floor", "conservative"])
+def test_lya_steps_with_the_sources_dropin(tmp_path, kind):
+    """SURVEY 8f rank 2 through the real executable: Nyx3d.dropin_src.ex also replaces Source/TimeStep/Nyx_update_state_with_sources.cpp
+    (nyx_sources_dropin.cpp: the fused source / floor / gravity kernel; with nyx.enforce_min_density_type = conservative the reference's loop of
+    FillPatch + one C-ABI call per iteration).  nyx.small_dens is raised into the density range of the 32^3 field (min 5.10e9, mean 6.29e9) so
+    that enforce_minimum_density acts in both steps; two coarse steps against the reference executable, plotfile against plotfile."""
+    exe = os.path.join(REAL, "Nyx3d.dropin_src.ex")
+    _need(exe, REFERENCE)
+    args = ["inputs.rt", "max_step=2", "amr.plot_int=2", "amr.check_int=-1", "amr.v=0", "nyx.v=2", "gravity.v=0", "particles.v=0",
+            "nyx.small_dens=5.2e9", f"nyx.enforce_min_density_type={kind}"]
+    res, outs = {}, {}
+    for tag, ex in (("ref", REFERENCE), ("b200", exe)):
+        d = tmp_path / tag
+        d.mkdir()
+        _stage(d)
+        rc, out = _run(ex, args, str(d))
+        assert rc == 0, out[-2000:]
+        res[tag], outs[tag] = _plot(str(d / "plt00002")), out
+    if kind == "conservative":
+        for tag in outs:   # the reference's own report of the loop, printed by both
+            assert outs[tag].count("After 1 iterations") == 2, tag
+        assert min(res["b200"]["density"].min(), res["ref"]["density"].min()) >= 5.2e9
+    for name, tol in (("density", 1e-9), ("xmom", None), ("rho_e", 1e-3), ("rho_E", 1e-3), ("Temp", 1e-3)):
+        if name not in res["ref"]:
+            continue
+        a, b = res["b200"][name], res["ref"][name]
+        if tol is None:
+            assert np.abs(a - b).max() < 1e-6 * np.abs(b).max(), name
+        else:
+            assert (np.abs(a - b) / np.abs(b)).max() < tol, (name, (np.abs(a - b) / np.abs(b)).max())

@@ -673,16 +673,108 @@ def test_enforce_minimum_density_multi_rank_protocol(hc_lib, port, host):
             assert np.array_equal(arrs[k][bi] if host else arrs[k][bi].cpu().numpy(), ref[k][bi]), (k, bi)
 
 
+@pytest.mark.parametrize("host", [False, True])
+def test_update_state_with_sources_conservative(hc_lib, port, host):
+    """nyx.enforce_min_density_type = "conservative" (Nyx::enforce_minimum_density_cons): the update as the reference's three sweeps on a
+    periodic 16^3 level cut into two boxes -- source update alone + minimum; iterations of the density redistribution, each after a FillPatch
+    of the two-ghost-cell border copy (emulated here: periodic wrap of the assembled level); gravity + the SDC reset of hydro_src(rho).  Every
+    array after every call equals the port's bit for bit (the port's iteration equals the reference's own per-cell functions,
+    tests/test_oracle_vs_reference.py); cells on the box faces are filled through the ghost cells; mass is conserved."""
+    import ctypes as C
+    from oracle import pyref
+    torch = _torch()
+    n, z = 16, 3.0
+    rng = np.random.default_rng(77)
+    target, small = util.cons_inputs(n, 741)
+    a_old = 1.0 / (1.0 + z); dt = synth.step_dt(z); a_new = synth.a_after(z, dt)
+    s_old = target * rng.uniform(0.8, 1.2, target.shape); s_old[0] = np.abs(s_old[0]) + small
+    ext = 0.01 * s_old / dt * rng.standard_normal(s_old.shape); ext[0] = 0.0
+    hs = 0.05 * s_old * rng.standard_normal(s_old.shape)
+    hs[0] = target[0] - s_old[0]                       # the source update lands on the crafted density (up to rounding)
+    grav = 1.0e3 * rng.standard_normal((3, n, n, n))
+    level = dict(s_old=s_old, s_new=rng.standard_normal(s_old.shape), ext_src=ext, hydro_src=hs, grav=grav, reset_src=np.full((1, n, n, n), -3.0))
+    boxes = [((0, 0, 0), (7, n - 1, n - 1)), ((8, 0, 0), (n - 1, n - 1, n - 1))]
+    cut = lambda a, b: np.ascontiguousarray(a[..., b[0][0]:b[1][0] + 1])       # noqa: E731
+    # ---- the port, box by box
+    P = {k: [cut(v, b) for b in boxes] for k, v in level.items()}
+    lib = port.lib
+    fp, l3 = C.POINTER(pyref.HcoFab), C.c_int * 3
+    lib.hco_sources_apply_box.restype = C.c_double
+    lib.hco_sources_apply_box.argtypes = [fp] * 4 + [l3, l3, C.c_double, C.c_double, C.c_double]
+    lib.hco_sources_finish_box.argtypes = [C.POINTER(pyref.HcoParams)] + [fp] * 4 + [l3, l3] + [C.c_double] * 5 + [C.c_int, C.c_int]
+    F = lambda k, bi: C.byref(pyref.fab_of(P[k][bi], boxes[bi][0]))             # noqa: E731
+    m_port = min(lib.hco_sources_apply_box(F("s_old", bi), F("s_new", bi), F("ext_src", bi), F("hydro_src", bi), l3(*b[0]), l3(*b[1]), dt, a_old, a_new)
+                 for bi, b in enumerate(boxes))
+    assert m_port < small
+    # ---- the CUDA path
+    prm = hc_lib.src_params(small_dens=small, small_temp=1.0e-2, min_density_type=1)
+    if host:
+        G = {k: [cut(v, b) for b in boxes] for k, v in level.items()}
+        mk = capi.fab_of_numpy
+    else:
+        G = {k: [torch.from_numpy(cut(v, b)).cuda() for b in boxes] for k, v in level.items()}
+        mk = capi.fab_of_torch
+    get = (lambda x: x) if host else (lambda x: x.cpu().numpy())
+    fabs = {k: [mk(G[k][bi], boxes[bi][0]) for bi in range(2)] for k in G}
+    tiles = [capi.make_box(*b) for b in boxes]
+    five = [fabs[k] for k in ("s_old", "s_new", "ext_src", "hydro_src", "grav")]
+    m = hc_lib.update_state_with_sources_batch(*five, tiles, dt, a_old, a_new, prm, host=host)
+    assert m == m_port
+    for bi in range(2):
+        assert np.array_equal(get(G["s_new"][bi]), P["s_new"][bi])          # the source update alone (no gravity yet)
+    with pytest.raises(Exception):                                          # the floor variant's second pass is not for this type
+        hc_lib.enforce_minimum_density_batch(*five, tiles, dt, a_old, a_new, prm, host=host)
+    mass0 = sum(x[0].sum() for x in P["s_new"])
+    it = 0
+    while m < small and it < 10:
+        whole = np.concatenate([get(x) for x in G["s_new"]], axis=3)
+        assert np.array_equal(whole, np.concatenate(P["s_new"], axis=3))
+        wb = util.fill_border(whole, 2)                                     # FillPatch: the caller's
+        sb = [np.ascontiguousarray(wb[..., b[0][0]:b[1][0] + 5]) for b in boxes]
+        sbl = [tuple(x - 2 for x in b[0]) for b in boxes]
+        ms = []
+        for bi, b in enumerate(boxes):
+            mm, bad = port.enforce_min_cons_iter(sb[bi], P["s_new"][bi], P["reset_src"][bi], b[0], b[1], small)
+            assert bad == 0
+            ms.append(mm)
+        sbg = sb if host else [torch.from_numpy(x).cuda() for x in sb]
+        m = hc_lib.enforce_min_density_cons_iter([mk(sbg[bi], sbl[bi]) for bi in range(2)], fabs["s_new"], fabs["reset_src"], tiles, prm, host=host)
+        assert m == min(ms), it
+        for bi in range(2):
+            assert np.array_equal(get(G["s_new"][bi]), P["s_new"][bi]) and np.array_equal(get(G["reset_src"][bi]), P["reset_src"][bi]), (it, bi)
+        it += 1
+    assert 2 <= it < 10 and m >= small
+    assert abs(sum(x[0].sum() for x in P["s_new"]) / mass0 - 1) < 1e-12
+    # ---- gravity and the SDC reset of hydro_src(rho)
+    pp = port.params()
+    for bi, b in enumerate(boxes):
+        P["hydro_src"][bi][0] = P["s_new"][bi][0] - P["s_old"][bi][0]       # Nyx_enforce_minimum_density.cpp:40-63
+        lib.hco_sources_finish_box(C.byref(pp), F("s_old", bi), F("s_new", bi), F("hydro_src", bi), F("grav", bi), l3(*b[0]), l3(*b[1]), dt, a_old, a_new,
+                                   small, 1.0e-2, 0, 1)
+    hc_lib.finish_state_with_sources_batch(*five, tiles, dt, a_old, a_new, prm, True, host=host)
+    if not host:
+        torch.cuda.synchronize()
+    for bi in range(2):
+        for k in ("s_new", "hydro_src", "reset_src", "s_old", "ext_src", "grav"):
+            assert np.array_equal(get(G[k][bi]), P[k][bi]), (k, bi)
+    # a border copy with fewer than two ghost cells is refused
+    with pytest.raises(Exception):
+        hc_lib.enforce_min_density_cons_iter(fabs["s_new"], fabs["s_new"], fabs["reset_src"], tiles, prm, host=host)
+
+
 def test_sources_argument_errors_and_async(hc_lib):
-    """conservative variant and wrong component counts are rejected; want_min=False does not synchronise and gives the same S_new"""
+    """an unknown enforce_min_density_type, the floor variant's second pass asked for the conservative type and wrong component counts are
+    rejected; want_min=False does not synchronise and gives the same S_new"""
     torch = _torch()
     d = util.sources_inputs(seed=940)
     slots = ("s_old", "s_new", "ext_src", "hydro_src", "grav", "reset_src")
     arrs = {k: [torch.from_numpy(x).cuda() for x in d[k]] for k in slots}
     fabs, tiles = _src_fabs(d, arrs)
     args = (fabs["s_old"], fabs["s_new"], fabs["ext_src"], fabs["hydro_src"], fabs["grav"], tiles, d["dt"], d["a_old"], d["a_new"])
+    with pytest.raises(capi.HcError, match="enforce_min_density_type"):
+        hc_lib.update_state_with_sources_batch(*args, hc_lib.src_params(small_dens=1.0, small_temp=1.0, min_density_type=2))
     with pytest.raises(capi.HcError, match="conservative"):
-        hc_lib.update_state_with_sources_batch(*args, hc_lib.src_params(small_dens=1.0, small_temp=1.0, min_density_type=1))
+        hc_lib.enforce_minimum_density_batch(*args, hc_lib.src_params(small_dens=1.0, small_temp=1.0, min_density_type=1))
     with pytest.raises(capi.HcError, match="6 components"):
         hc_lib.update_state_with_sources_batch(fabs["s_old"], fabs["s_new"], fabs["ext_src"], fabs["hydro_src"], fabs["reset_src"], tiles, d["dt"], d["a_old"],
                                                d["a_new"], hc_lib.src_params())

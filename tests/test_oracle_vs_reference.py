@@ -185,3 +185,29 @@ def test_update_state_with_sources_bitwise(reference, port, low):
         else:
             assert np.array_equal(p["hydro_src"][bi][0], d["hydro_src"][bi][0])
     assert (n_floor >= low) if low else n_floor == 0     # about 3/4 of the 3 x low prepared cells end below small_dens
+
+
+@pytest.mark.parametrize("n,seed,ng_new", [(12, 701, 1), (9, 702, 0)])
+def test_enforce_min_density_conservative_iterations_bitwise(reference, port, n, seed, ng_new):
+    """nyx.enforce_min_density_type = "conservative": the port's restatement of one iteration of Nyx::enforce_minimum_density_cons against the
+    reference's own per-cell functions (compute_mu_for_enforce_min / create_update_for_minimum through oracle/_ref), iterated with a periodic
+    FillPatch until the density is enforced: every iteration bit for bit, total mass conserved"""
+    s0, small = util.cons_inputs(n, seed)
+    lo, hi = (0, 0, 0), (n - 1, n - 1, n - 1)
+    pad = lambda a, g: util.fill_border(a, g) if g else a.copy()   # noqa: E731
+    sn_ref, sn_port = pad(s0, ng_new), pad(s0, ng_new)
+    inner = (slice(None),) + (slice(ng_new, ng_new + n),) * 3
+    rs_ref, rs_port = np.full((1, n, n, n), -3.0), np.full((1, n, n, n), -3.0)
+    mass0 = s0[0].sum()
+    m = s0[0].min()
+    it = 0
+    while m < small and it < 10:
+        sb = util.fill_border(sn_port[inner], 2)
+        m_ref = reference.enforce_min_cons_iter(sb.copy(), sn_ref, rs_ref, lo, hi, small, ng_new=ng_new)
+        m, bad = port.enforce_min_cons_iter(sb, sn_port, rs_port, lo, hi, small, ng_new=ng_new)
+        assert bad == 0
+        assert m == m_ref and np.array_equal(sn_ref, sn_port) and np.array_equal(rs_ref, rs_port), it
+        it += 1
+    assert 2 <= it < 10 and m >= small                # the cluster needs more than one iteration
+    assert abs(sn_port[inner][0].sum() / mass0 - 1) < 1e-12       # density only moves between cells
+    assert (rs_port != -3.0).all()

@@ -163,3 +163,33 @@ class Harness:
 
 def stats_equal(cs, port_stats):
     return all(np.array_equal(cs[f], port_stats[:, i]) for i, f in enumerate(capi.CELLSTAT_FIELDS))
+
+
+def cons_inputs(n, seed, nlow=40):
+    """a periodic n^3 state for the "conservative" variant of enforce_minimum_density: lognormal density with `nlow` cells pushed below
+    small_dens -- isolated ones, adjacent pairs, cells on the box faces and one cell that one iteration cannot fill -- momenta and
+    energies random.  Returns (s_new (6, n, n, n), small_dens)"""
+    rng = np.random.default_rng(seed)
+    s = np.empty((6, n, n, n))
+    s[0] = np.exp(rng.normal(0.0, 0.7, (n, n, n)))
+    small = 0.05
+    s[0] = np.maximum(s[0], 1.2 * small)
+    for c in (1, 2, 3):
+        s[c] = s[0] * rng.normal(0.0, 1.0, (n, n, n))
+    s[5] = s[0] * np.exp(rng.normal(0.0, 0.5, (n, n, n)))
+    s[4] = s[5] + 0.5 * (s[1] ** 2 + s[2] ** 2 + s[3] ** 2) / s[0]
+    idx = rng.integers(0, n, (nlow, 3))
+    idx[:6, 0] = 0; idx[6:10, 1] = n - 1; idx[10:12, 2] = 0            # on the faces of the box: filled through the ghost cells
+    for q, (k, j, i) in enumerate(idx):
+        s[0, k, j, i] = small * rng.uniform(-0.5, 0.99)                # below small_dens (some negative)
+        if q % 5 == 0:
+            s[0, k, j, (i + 1) % n] = small * rng.uniform(0.1, 0.9)    # an adjacent pair
+    k, j, i = n // 2, n // 2, n // 2
+    s[0, k - 1:k + 2, j - 1:j + 2, i - 1:i + 2] = small * 2.0          # a cell whose neighbours cannot cover its need in one iteration
+    s[0, k, j, i] = -0.5 * small                                       # (each gives a sixth of its excess over 1.01 small_dens): two iterations
+    return s, small
+
+
+def fill_border(valid, ng):
+    """periodic FillPatch of one box that covers the whole domain: (ncomp, n, n, n) -> (ncomp, n + 2 ng, ...)"""
+    return np.ascontiguousarray(np.pad(valid, ((0, 0), (ng, ng), (ng, ng), (ng, ng)), mode="wrap"))
