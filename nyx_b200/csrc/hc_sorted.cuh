@@ -24,7 +24,8 @@ namespace sorted {
 // 364 bytes per lane on the Strang path, 420 on the SDC path: 384 lanes fit the 164 KB shared-memory carve-out, which leaves the L1 92 KB
 // for the rate tables and the stack (round 1: 496 / 592 bytes, 196 / 228 KB carve-out, 60 / 28 KB of L1).
 #if !defined(HC_SORT_FINE)
-#define HC_SORT_FINE 2   // (3: additionally split by "this step attempt reaches tout": measured 56.26 vs 56.04 ms Strang, 88.07 vs 88.75 ms SDC at 256^3 -- no gain, profiles/r2_s10_sortkey_laststep.log)
+#define HC_SORT_FINE 2   // (3: additionally split by "this step attempt reaches tout": measured 56.26 vs 56.04 ms Strang, 88.07 vs 88.75 ms SDC at 256^3 -- no gain, profiles/r2_s10_sortkey_laststep.log;
+                         //  Newton-residual lanes split by first / later iteration of the attempt: 55.5 vs 55.5 ms, 88.0 vs 87.8 ms -- no gain, profiles/r2_s20_sortkey_variants.log)
 #endif
 #if HC_SORT_FINE == 3
 // (order q in {1, 2, 3+}) x (qwait == 1 or not: the step that prepares an order change) x (last step or not: a lane whose step attempt
@@ -125,6 +126,9 @@ __device__ __forceinline__ int sort_key(unsigned w0, unsigned w1) {
 // B work split: [16] load lane [17] resume + store_cell [18] refill [19] write back; [24..31] B work cycles of the warps whose first lane has
 // sort key 0..7, [32..39] number of such warp-rounds, [40..47] their active lanes in resume()
 __device__ unsigned long long g_phase[48];
+// bookkeeping phase by the classes of a warp's first and last lane (idx = 8 * first + last): [idx] cycles, [64 + idx] warp-rounds,
+// [128 + idx] rounds in which such a warp was the slowest of its CTA, [192 + idx] its cycles then
+__device__ unsigned long long g_mix[256];
 #define HC_TICK(slot) do { const long long t_ = clock64(); ph[slot] += (unsigned long long)(t_ - t_last); t_last = t_; } while (0)
 #else
 #define HC_TICK(slot) do { } while (0)
@@ -160,6 +164,8 @@ __global__ void __launch_bounds__(LANES, HC_SORTED_CTAS) hc_sorted_kernel(const 
     tot.iters_attempts = 0ull; tot.n_eos = 0u; tot.s_pair = s_pair;
     __syncthreads();
 #if defined(HC_PHASE_TIMING)
+    __shared__ unsigned long long s_slow;
+    if (tid == 0) s_slow = 0ull;
     unsigned long long ph[48];
 #pragma unroll
     for (int i = 0; i < 48; ++i) ph[i] = 0ull;
@@ -196,6 +202,7 @@ __global__ void __launch_bounds__(LANES, HC_SORTED_CTAS) hc_sorted_kernel(const 
 #if defined(HC_PHASE_TIMING)
             const long long t_b0 = clock64();
             const int key0 = key_class(__shfl_sync(0xffffffffu, sort_key<LaneT>(io.w(LaneT::WS_W0), io.w(LaneT::WS_W1)), 0));
+            const int key31 = key_class(__shfl_sync(0xffffffffu, sort_key<LaneT>(io.w(LaneT::WS_W0), io.w(LaneT::WS_W1)), 31));
 #endif
             const bool act0 = ln.active();
             const unsigned rmask = __ballot_sync(0xffffffffu, act0);
@@ -297,6 +304,11 @@ __global__ void __launch_bounds__(LANES, HC_SORTED_CTAS) hc_sorted_kernel(const 
                 const int nact = __popc(rmask);
 #pragma unroll
                 for (int kk = 0; kk < 8; ++kk) if (key0 == kk) { ph[24 + kk] += (unsigned long long)(t_b1 - t_b0); ph[32 + kk] += 1; ph[40 + kk] += nact; }
+                if (lane_id == 0) {
+                    const int idx = key0 * 8 + key31;
+                    atomicAdd(&g_mix[idx], (unsigned long long)(t_b1 - t_b0)); atomicAdd(&g_mix[64 + idx], 1ull);
+                    atomicMax(&s_slow, ((unsigned long long)(t_b1 - t_b0) << 6) | (unsigned long long)idx);
+                }
             }
 #endif
         }
@@ -311,6 +323,13 @@ __global__ void __launch_bounds__(LANES, HC_SORTED_CTAS) hc_sorted_kernel(const 
             if (rank == 0) s_cnt[key * L::WARPS + warp] = __popc(same);
             HC_TICK(20);
             const bool any_active = __syncthreads_or(active_after);
+#if defined(HC_PHASE_TIMING)
+            if (tid == 0) {
+                const unsigned long long v = s_slow;
+                atomicAdd(&g_mix[128 + (int)(v & 63ull)], 1ull); atomicAdd(&g_mix[192 + (int)(v & 63ull)], v >> 6);
+                s_slow = 0ull;
+            }
+#endif
             HC_TICK(3);
             if (!any_active) break;   // nothing in flight and the queue is empty
             // every warp computes its own bases: lane kk sums the counts of key kk over the warps (and over the warps before this one)

@@ -1680,6 +1680,13 @@ int hc_debug_phase(unsigned long long* out48) {
     CUDA_TRY(cudaMemcpyToSymbol(sorted::g_phase, zero, sizeof zero));
     return HC_OK;
 }
+int hc_debug_mix(unsigned long long* out256) {
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpyFromSymbol(out256, sorted::g_mix, 256 * sizeof(unsigned long long)));
+    static unsigned long long zero[256] = {0};
+    CUDA_TRY(cudaMemcpyToSymbol(sorted::g_mix, zero, sizeof zero));
+    return HC_OK;
+}
 int hc_debug_stage(unsigned long long* out16) {
     CUDA_TRY(cudaDeviceSynchronize());
     CUDA_TRY(cudaMemcpyFromSymbol(out16, g_stage, 16 * sizeof(unsigned long long)));

@@ -62,3 +62,17 @@ if hasattr(hc.lib, "hc_debug_stage"):
     print("resume() of the all-LSETUP warps, share of cycles per stage:")
     for i in range(16):
         print(f"    {nm[i]:26s} {100.0 * v[i] / tot:6.2f} %")
+if hasattr(hc.lib, "hc_debug_mix"):
+    import ctypes
+    buf = (ctypes.c_ulonglong * 256)()
+    hc.lib.hc_debug_mix(buf)
+    v = [int(x) for x in buf]
+    keys = ["NEWTON", "SETUP_REQ", "LSETUP", "HIN", "INIT", "ETEST", "FINAL", "IDLE"]
+    nwr, nslow = max(sum(v[64:128]), 1), max(sum(v[128:192]), 1)
+    print("bookkeeping phase by the classes of a warp's (first, last) lane: share of warp-rounds, mean cycles | share of the rounds in which it was the CTA's slowest warp, mean cycles then")
+    for i in range(64):
+        if v[64 + i] * 200 > nwr or v[128 + i] * 100 > nslow:
+            a, b = keys[i // 8], keys[i % 8]
+            slow = f"{100.0 * v[128 + i] / nslow:5.1f} %  {v[192 + i] / max(v[128 + i], 1):8.0f}" if v[128 + i] else "    -"
+            print(f"    {a:10s} {b:10s} {100.0 * v[64 + i] / nwr:5.1f} %  {v[i] / max(v[64 + i], 1):8.0f} | {slow}")
+    print(f"  mean cycles of the slowest warp of a CTA-round: {sum(v[192:256]) / nslow:.0f}")
