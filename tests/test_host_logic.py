@@ -239,6 +239,26 @@ def test_cabi_fails_loudly_without_device(built):
     with pytest.raises(capi.HcError):
         hc.compute_new_temp_batch([capi.fab_of_numpy(state, (0, 0, 0))], [capi.fab_of_numpy(diag, (0, 0, 0))], [capi.make_box((0, 0, 0), (3, 3, 3))],
                                   0.25, 1e-2, 1e9, 0)
+    # round-2 entry points: the conservative variant's iteration / finish calls and the SAVE_REACT overload
+    prm_c = hc.src_params(small_dens=d["small_dens"], small_temp=d["small_temp"], min_density_type=1)
+    n = 6
+    sn = np.ones((6, n, n, n)); sb = np.ones((6, n + 4, n + 4, n + 4)); rs = np.zeros((1, n, n, n))
+    tl = [capi.make_box((0, 0, 0), (n - 1,) * 3)]
+    for host in (True, False):
+        with pytest.raises(capi.HcError):
+            hc.enforce_min_density_cons_iter([capi.fab_of_numpy(sb, (-2, -2, -2))], [capi.fab_of_numpy(sn, (0, 0, 0))], [capi.fab_of_numpy(rs, (0, 0, 0))],
+                                             tl, prm_c, host=host)
+        with pytest.raises(capi.HcError):
+            hc.finish_state_with_sources_batch(fabs["s_old"], fabs["s_new"], fabs["ext_src"], fabs["hydro_src"], fabs["grav"], tiles, d["dt"],
+                                               d["a_old"], d["a_new"], prm_c, True, host=host)
+    assert (sn == 1.0).all()
+    sd = util.sdc_inputs(3.0, 4, 5, 0.05)
+    six = [[capi.fab_of_numpy(sd[k], (0, 0, 0))] for k in ("s_old", "diag", "s_new", "hydro_src", "reset_src", "ir")]
+    react = [[capi.fab_of_numpy(np.zeros((c, 4, 4, 4)), (0, 0, 0))] for c in (7, 7, 9)]
+    with pytest.raises(capi.HcError):
+        hc.integrate_struct_react_host(*six, *react, [capi.make_box((0, 0, 0), (3, 3, 3))], sd["a"], sd["a_end"], sd["dt"], 0)
+    with pytest.raises(capi.HcError):
+        hc.integrate_struct_react_batch(*six, *react, [capi.make_box((0, 0, 0), (3, 3, 3))], sd["a"], sd["a_end"], sd["dt"], 0)
     assert all(np.array_equal(x, y) for x, y in zip(before, d["s_new"]))
     with pytest.raises(capi.HcError, match="missing"):
         capi.NyxHC(path="/nonexistent/libnyx_hc.so")
