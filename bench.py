@@ -428,7 +428,7 @@ class PathBench:
         t = ctx["allmax"](t)
         return {"value": ncell_global * n / t, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": n,
                 "ms_per_step": 1e3 * t / n, "h2d_gbs_this_rank": h2d * n / t_loc / 1e9, "d2h_gbs_this_rank": d2h * n / t_loc / 1e9,
-                "api": "hc_integrate_%s_host on pinned host FABs (H2D / kernel / D2H pipelined over 8 groups of boxes, kernels of consecutive groups on alternating streams)" % self.path,
+                "api": "hc_integrate_%s_host on pinned host FABs (H2D / kernel / D2H pipelined over groups of boxes -- 1/64, 1/32, 1/16, 1/8 ... of the cells, halving again at the end -- with the kernels of consecutive groups on alternating streams)" % self.path,
                 "n_failed": st_h.n_failed}
 
     def free(self):

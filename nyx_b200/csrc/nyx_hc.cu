@@ -858,7 +858,8 @@ HostPipe g_pipe[64];
 constexpr int HOST_GROUPS = HC_HOST_GROUPS;
 // measurement knob: NYX_HC_HOST_ONE_COMP_STREAM=1 puts every group's kernel on the same stream (the round-1 pipeline)
 #if !defined(HC_HOST_TAPER)
-#define HC_HOST_TAPER 1
+#define HC_HOST_TAPER 2   // 0: equal groups; 1: first group half a share; 2: geometric ramps at both ends (512^3 step end to end, profiles/r2_s23_host_taper.log:
+                          //    Strang 440.0 against 441.3 ms, SDC 703.5 against 715.5 ms with 1)
 #endif
 constexpr bool HOST_TAPER = (HC_HOST_TAPER != 0);
 size_t fab_doubles(const HcFab& f) { return (size_t)f.nstride * f.ncomp; }
@@ -980,7 +981,20 @@ int run_host(int path, int ntiles, std::vector<HostSlot>& slots, const HcBox* ti
     for (int t0 = 0; t0 < ntiles && rc == HC_OK; ++group) {
         // the first group is half a share: its H2D is not hidden behind any kernel; the last group then is the remaining half share, whose
         // D2H is not hidden either (measured: 496.8 ms instead of 507.0 ms per 512^3 step; a finer ramp 1/32, 1/16, 1/8 ... 3/32, 1/16: 495.5 ms, not kept)
-        const long long share = (group == 0 && HOST_TAPER) ? std::max<long long>(per_group / 2, 1) : per_group;
+        long long share = (group == 0 && HOST_TAPER) ? std::max<long long>(per_group / 2, 1) : per_group;
+#if HC_HOST_TAPER == 2
+        // geometric ramps at both ends: the first H2D and the last D2H are the only transfers no kernel hides, so the first groups take
+        // 1/64, 1/32, 1/16 of the cells and the last ones half of what is left each (the drain tail of a small group's kernel overlaps the next
+        // kernel: consecutive groups run on alternating streams)
+        {
+            long long done = 0;
+            for (int t = 0; t < t0; ++t) done += cells[t];
+            const long long unit = std::max<long long>(total / 64, 1);
+            const long long head = (group < 30) ? (unit << std::min(group, 20)) : per_group;
+            const long long tail = std::max<long long>((total - done) / 2, unit);
+            share = std::min(per_group, std::min(head, tail));
+        }
+#endif
         int t1 = t0; long long acc = 0;
         while (t1 < ntiles && (t1 == t0 || acc + cells[t1] <= share || shares_fab(t1, t1 - 1))) acc += cells[t1++];
         const int n = t1 - t0;
