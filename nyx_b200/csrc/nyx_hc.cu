@@ -700,6 +700,18 @@ int set_smem_attr(KernelT kernel, DeviceTables& dt, int slot, size_t bytes) {
     return HC_OK;
 }
 
+// stream-ordered scratch of a launcher, released on EVERY exit path (early error returns included)
+struct StreamScratch {
+    cudaStream_t stream;
+    void* p[4] = {nullptr, nullptr, nullptr, nullptr};
+    int n = 0;
+    explicit StreamScratch(cudaStream_t s) : stream(s) {}
+    StreamScratch(const StreamScratch&) = delete;
+    StreamScratch& operator=(const StreamScratch&) = delete;
+    void own(void* q) { if (q && n < 4) p[n++] = q; }
+    ~StreamScratch() { for (int i = 0; i < n; ++i) cudaFreeAsync(p[i], stream); }
+};
+
 // Common launcher: build tile descriptors, stream-ordered scratch, launch, optionally read the statistics back.
 // `ext_dstats` (device, 14 x u64, zeroed by the caller): accumulate the statistics there instead (several launches of one call).
 struct EosOpts {
@@ -752,7 +764,9 @@ int launch(int path, int ntiles, const HcFab* const* fabs, int nf, const HcBox* 
     const size_t react_bytes = h_react.size() * sizeof(HcFab);
     const size_t scratch_bytes = 256 + tiles_bytes + react_bytes;   // [queue u64][pad][stats 14 x u64][pad] [tiles] [react FABs]
     char* scratch = nullptr;
+    StreamScratch owned(stream);
     CUDA_TRY(cudaMallocAsync((void**)&scratch, scratch_bytes, stream));
+    owned.own(scratch);
     CUDA_TRY(cudaMemsetAsync(scratch, 0, 256, stream));
     if (int rc = copy_small_h2d(dev, scratch + 256, h_tiles.data(), tiles_bytes, stream)) return rc;
     // SAVE_REACT: the per-cell record of the REACT kernel and (unless the caller asked for them anyway) the per-cell counters
@@ -761,7 +775,12 @@ int launch(int path, int ntiles, const HcFab* const* fabs, int nf, const HcBox* 
     if (react) {
         if (int rc = copy_small_h2d(dev, scratch + 256 + tiles_bytes, h_react.data(), react_bytes, stream)) return rc;
         CUDA_TRY(cudaMallocAsync((void**)&react_raw, (size_t)ncells * 4 * sizeof(double), stream));
-        if (!cell_stats) { CUDA_TRY(cudaMallocAsync((void**)&own_cell_stats, (size_t)ncells * sizeof(HcCellStat), stream)); cell_stats = own_cell_stats; }
+        owned.own(react_raw);
+        if (!cell_stats) {
+            CUDA_TRY(cudaMallocAsync((void**)&own_cell_stats, (size_t)ncells * sizeof(HcCellStat), stream));
+            owned.own(own_cell_stats);
+            cell_stats = own_cell_stats;
+        }
     }
 
     KernelArgs a{};
@@ -820,10 +839,7 @@ int launch(int path, int ntiles, const HcFab* const* fabs, int nf, const HcBox* 
             g_last_drain_ms = (tm[0] != 0 && t_end > t_empty) ? 1e-6 * (double)(t_end - t_empty) : 0.0;
         }
     }
-    if (react_raw) CUDA_TRY(cudaFreeAsync(react_raw, stream));
-    if (own_cell_stats) CUDA_TRY(cudaFreeAsync(own_cell_stats, stream));
-    CUDA_TRY(cudaFreeAsync(scratch, stream));
-    return HC_OK;
+    return HC_OK;   // `owned` releases the scratch, stream-ordered after the kernels
 }
 
 // ---- host-buffer entry points: staged and pipelined --------------------------------------------------------------------
@@ -1098,9 +1114,15 @@ int stage_tiles(int ntiles, const HcFab* const* fabs, int nf, const HcBox* tiles
     if (ncells == 0) return HC_OK;
     const size_t tiles_bytes = h_tiles.size() * sizeof(TileDesc);
     CUDA_TRY(cudaMallocAsync((void**)&scratch, 256 + tiles_bytes, stream));
-    CUDA_TRY(cudaMemsetAsync(scratch, 0xff, 256, stream));     // the minimum key starts at its largest value
-    int dev; if (int rc = current_device(dev)) return rc;
-    return copy_small_h2d(dev, scratch + 256, h_tiles.data(), tiles_bytes, stream);
+    if (cudaMemsetAsync(scratch, 0xff, 256, stream) != cudaSuccess) {     // the minimum key starts at its largest value
+        cudaFreeAsync(scratch, stream); scratch = nullptr;
+        set_err("cudaMemsetAsync failed"); return HC_ERR_CUDA;
+    }
+    int dev = 0;
+    int rc = current_device(dev);
+    if (rc == HC_OK) rc = copy_small_h2d(dev, scratch + 256, h_tiles.data(), tiles_bytes, stream);
+    if (rc != HC_OK) { cudaFreeAsync(scratch, stream); scratch = nullptr; }
+    return rc;
 }
 
 SrcArgs make_src_args(double dt, double a_old, double a_new, const HcSrcParams& p) {
@@ -1136,6 +1158,8 @@ int launch_sources(int mode, int ntiles, const HcFab* const* fabs, const HcBox* 
     int sms = 0; if (int rc = sm_count_of(dev, sms)) return rc;
     char* scratch; int n_used; long long ncells;
     if (int rc = stage_tiles(ntiles, fabs, 5, tiles, stream, scratch, n_used, ncells)) return rc;
+    StreamScratch owned(stream);
+    owned.own(scratch);
     if (min_dens_out) *min_dens_out = DBL_MAX;
     if (ncells == 0) return HC_OK;
     SrcArgs a = make_src_args(dt, a_old, a_new, p);
@@ -1158,7 +1182,6 @@ int launch_sources(int mode, int ntiles, const HcFab* const* fabs, const HcBox* 
         CUDA_TRY(cudaStreamSynchronize(stream));
         *min_dens_out = dens_from_key(key);
     }
-    CUDA_TRY(cudaFreeAsync(scratch, stream));
     return HC_OK;
 }
 
@@ -1179,14 +1202,15 @@ int launch_fab_op(int op, int ntiles, const HcFab* dst, int dcomp, const HcFab* 
     const HcFab* fabs[2] = {dst, src};
     char* scratch; int n_used; long long ncells, nchunks = 0;
     if (int rc = stage_tiles(ntiles, fabs, 2, tiles, stream, scratch, n_used, ncells, -1, &nchunks)) return rc;
-    if (ncells == 0 || ncomp == 0) { if (scratch) CUDA_TRY(cudaFreeAsync(scratch, stream)); return HC_OK; }
+    StreamScratch owned(stream);
+    owned.own(scratch);
+    if (ncells == 0 || ncomp == 0) return HC_OK;
     FabOpArgs a{};
     a.tiles = reinterpret_cast<const TileDesc*>(scratch + 256);
     a.ntiles = n_used; a.ncells = ncells; a.nchunks = nchunks; a.scomp = scomp; a.dcomp = dcomp; a.ncomp = ncomp; a.op = op;
     const int grid = stream_grid(nchunks, 8, sms);   // 8 warps per CTA, one chunk per warp and pass
     hc_fab_op_kernel<<<grid, 256, 0, stream>>>(a);
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaFreeAsync(scratch, stream));
     return HC_OK;
 }
 
@@ -1464,6 +1488,8 @@ int launch_cons_iter(int ntiles, const HcFab* const* fabs, const HcBox* tiles, c
     int sms = 0; if (int rc = sm_count_of(dev, sms)) return rc;
     char* scratch; int n_used; long long ncells;
     if (int rc = stage_tiles(ntiles, fabs, p.sdc ? 3 : 2, tiles, stream, scratch, n_used, ncells)) return rc;
+    StreamScratch owned(stream);
+    owned.own(scratch);
     if (ncells == 0) return HC_OK;
     ConsArgs a{};
     a.tiles = reinterpret_cast<const TileDesc*>(scratch + 256);
@@ -1471,7 +1497,6 @@ int launch_cons_iter(int ntiles, const HcFab* const* fabs, const HcBox* tiles, c
     const int grid = (int)std::min<long long>((ncells + 255) / 256, (long long)sms * 8);
     hc_min_dens_cons_kernel<<<grid, 256, 0, stream>>>(a);
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaFreeAsync(scratch, stream));
     return HC_OK;
 }
 int finish_cons(unsigned long long* dmm, cudaStream_t stream, double* min_after) {
@@ -1627,6 +1652,8 @@ int hc_init_zhi_batch(int ntiles, const HcFab* diag, const HcFab* zhi, int ratio
     const HcFab* fabs[2] = {diag, zhi};
     char* scratch; int n_used; long long ncells;
     if (int rc = stage_tiles(ntiles, fabs, 2, tiles, stream, scratch, n_used, ncells, 1)) return rc;   // containment of the fine tile: diag only
+    StreamScratch owned(stream);
+    owned.own(scratch);
     if (ncells == 0) return HC_OK;
     ZhiArgs a{};
     a.tiles = reinterpret_cast<const TileDesc*>(scratch + 256);
@@ -1634,7 +1661,6 @@ int hc_init_zhi_batch(int ntiles, const HcFab* diag, const HcFab* zhi, int ratio
     const int grid = (int)std::min<long long>((ncells + 255) / 256, (long long)sms * 16);
     hc_init_zhi_kernel<<<grid, 256, 0, stream>>>(a);
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaFreeAsync(scratch, stream));
     return HC_OK;
 }
 
