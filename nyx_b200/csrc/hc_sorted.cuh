@@ -23,38 +23,19 @@ namespace sorted {
 // (the 22 Nordsieck / coefficient doubles first) and LaneT::WS_N 32-bit words per lane, structure of arrays [slot][lane].
 // 364 bytes per lane on the Strang path, 420 on the SDC path: 384 lanes fit the 164 KB shared-memory carve-out, which leaves the L1 92 KB
 // for the rate tables and the stack (round 1: 496 / 592 bytes, 196 / 228 KB carve-out, 60 / 28 KB of L1).
-#if !defined(HC_SORT_FINE)
-#define HC_SORT_FINE 2   // (3: additionally split by "this step attempt reaches tout": measured 56.26 vs 56.04 ms Strang, 88.07 vs 88.75 ms SDC at 256^3 -- no gain, profiles/r2_s10_sortkey_laststep.log;
-                         //  Newton-residual lanes split by first / later iteration of the attempt: 55.5 vs 55.5 ms, 88.0 vs 87.8 ms -- no gain, profiles/r2_s20_sortkey_variants.log)
-#endif
-#if HC_SORT_FINE == 3
-// (order q in {1, 2, 3+}) x (qwait == 1 or not: the step that prepares an order change) x (last step or not: a lane whose step attempt
-// reaches tout skips the whole set-up of the next step and runs the finalize step, the store of the cell and the refill of its lane
-// instead -- DRAM round trips and, on the SDC path, ~10 divisions) x (Newton-residual lane | Jacobian-setup lane, side by side)
-constexpr int NSUB = 6;
-enum Key { K_NEWTON = 0, K_SETUP_REQ = 4 * NSUB, K_HIN, K_INIT, K_ETEST, K_FINAL, K_IDLE, NKEY };
-constexpr int K_LSETUP = 1;
-#elif HC_SORT_FINE
-// the step-completing lanes are split further by (order q, qwait), which decide loop trip counts and branches of their chain
-// (measured in one gpurun call, best of 6, twice: 68.43 / 68.48 ms against 69.48 / 71.87 ms with the 8 plain keys; HC_SORT_FINE == 2
-// interleaves the two step-completing phases within each (q, qwait) class: 62.15 / 61.60 ms against 64.66 / 65.86 ms for == 1)
+// Sort keys.  The step-completing lanes (Newton-residual and Jacobian-setup phases) are split further by (order q, qwait), which decide loop
+// trip counts and branches of their chain, and the two phases are interleaved within each (q, qwait) class: a Newton-residual lane sits
+// next to the Jacobian-setup lanes of the same class -- they differ in their first two stages only and share the long tail of the chain.
+// Measured, each within one gpurun call: 8 plain keys 69.5 ms -> (q, qwait) classes 68.4 ms -> interleaved 61.6 ms
+// (256^3 Strang, round 1); no gain from splitting further by "this attempt reaches tout" (profiles/r2_s10_sortkey_laststep.log) or by
+// first / later Newton iteration (profiles/r2_s20_sortkey_variants.log); (qwait, q) instead of (q, qwait) order: 0.99x / 0.965x
+// (profiles/r2_s22_subkey_transposed.log).
 constexpr int NSUB = 9;   // (min(q,3)-1) * 3 + (min(qwait,3)-1)
-enum Key { K_NEWTON = 0, K_LSETUP = NSUB, K_SETUP_REQ = 2 * NSUB, K_HIN, K_INIT, K_ETEST, K_FINAL, K_IDLE, NKEY };
-#else
-constexpr int NSUB = 1;
-constexpr int NKEY = 8;   // sort keys, in the order the warps will process them
-enum Key { K_NEWTON = 0, K_SETUP_REQ, K_LSETUP, K_HIN, K_INIT, K_ETEST, K_FINAL, K_IDLE };
-#endif
+enum Key { K_NEWTON = 0, K_SETUP_REQ = 2 * NSUB, K_HIN, K_INIT, K_ETEST, K_FINAL, K_IDLE, NKEY };
 static_assert(NKEY <= 32, "one lane per key in the base computation");
 // the 8 integrator phases behind the keys (diagnostics): NEWTON, SETUP_REQ, LSETUP, HIN, INIT, ETEST, FINAL, IDLE
 __device__ __forceinline__ int key_class(int key) {
-#if HC_SORT_FINE >= 2
     return (key < K_SETUP_REQ) ? ((key & 1) ? 2 : 0) : (key == K_SETUP_REQ) ? 1 : 3 + (key - K_HIN);
-#elif HC_SORT_FINE
-    return (key < K_LSETUP) ? 0 : (key < K_SETUP_REQ) ? 2 : (key == K_SETUP_REQ) ? 1 : 3 + (key - K_HIN);
-#else
-    return key;
-#endif
 }
 
 // Both accessors index the extern __shared__ array ITSELF with an integer lane number: through pointers kept in a struct the compiler
@@ -93,25 +74,11 @@ template <class LaneT>
 __device__ __forceinline__ int sort_key(unsigned w0, unsigned w1) {
     const int pc = (int)(w0 & 15u);
     const bool callSetup = (w1 >> 8) & 1u, res_at_top = (w1 >> 9) & 1u;
-#if HC_SORT_FINE == 3
     const int q = (int)((w0 >> 4) & 15u), qwait = (int)((w0 >> 12) & 15u);
-    const int sub = ((min(max(q, 1), 3) - 1) * 2 + (qwait == 1 ? 0 : 1)) * 2 + (int)((w1 >> 21) & 1u);
-#elif HC_SORT_FINE
-    const int q = (int)((w0 >> 4) & 15u), qwait = (int)((w0 >> 12) & 15u);
-    const int sub = (min(max(q, 1), 3) - 1) * 3 + (min(max(qwait, 1), 3) - 1);   // (qwait class major, q class minor: 0.99x Strang, 0.965x SDC, profiles/r2_s22_subkey_transposed.log)
-#else
-    const int sub = 0;
-#endif
+    const int sub = (min(max(q, 1), 3) - 1) * 3 + (min(max(qwait, 1), 3) - 1);
     switch (pc) {
-#if HC_SORT_FINE >= 2
-    // the two step-completing phases interleaved: key = 2 * (q, qwait class) + phase, so that a Newton-residual lane sits next to the
-    // Jacobian-setup lanes of the same order -- they differ in their first two stages only and share the long tail of the chain
     case PC_NLS_RES: return (res_at_top && callSetup) ? K_SETUP_REQ : K_NEWTON + 2 * sub;
     case PC_LSETUP_F: return K_NEWTON + 2 * sub + 1;
-#else
-    case PC_NLS_RES: return (res_at_top && callSetup) ? K_SETUP_REQ : K_NEWTON + sub;
-    case PC_LSETUP_F: return K_LSETUP + sub;
-#endif
     case PC_HIN_F: return K_HIN;
     case PC_INIT_F0: return K_INIT;
     case PC_ETEST_F: return K_ETEST;
@@ -173,18 +140,15 @@ __global__ void __launch_bounds__(LANES, HC_SORTED_CTAS) hc_sorted_kernel(const 
     const long long t_begin = t_last;
 #endif
 
-    // Round structure (two CTA barriers per SORTED round, none otherwise):
+    // Round structure (two CTA barriers per round):
     //   B   thread t runs the bookkeeping of lane `my` (stores a finished cell, refills an idle lane);
-    //   S   (every HC_SORT_EVERY-th round) counting sort by the keys the threads hold in registers: counts, barrier (which also decides
-    //       termination), bases + order, barrier; thread t adopts lane order[t];
+    //   S   counting sort by the keys the threads hold in registers: counts, barrier (which also decides termination), bases + order,
+    //       barrier; thread t adopts lane order[t];
     //   R   thread t evaluates the request of ITS lane -- the lane whose bookkeeping it runs next, so no barrier separates R from B.
-    // In an unsorted round a warp keeps its lanes: a warp sorted into the long step-completing class has the short "request the Jacobian
-    // setup" class next, so over a pair of rounds the warps carry about the same bookkeeping load and meet at the barrier together.
-#if !defined(HC_SORT_EVERY)
-#define HC_SORT_EVERY 1
-#endif
+    // (Sorting only every 2nd / 3rd round lets the warps drift apart, evaluation code then runs next to bookkeeping code: 0.81x / 0.72x,
+    // profiles/r2_s6_round_structure.log.)
     int my = tid;
-    for (unsigned round = 0;; ++round) {
+    for (;;) {
         // ================= phase B: bookkeeping of lane `my`
         bool active_after;
         int key;
@@ -213,15 +177,6 @@ __global__ void __launch_bounds__(LANES, HC_SORTED_CTAS) hc_sorted_kernel(const 
             ln.dbg_on = (key0 == HC_DBG_CLASS) && (key_class(__shfl_sync(0xffffffffu, sort_key<LaneT>(io.w(LaneT::WS_W0), io.w(LaneT::WS_W1)), 31)) == HC_DBG_CLASS);   // stage timing: warps made of one phase only
             ln.dbg_last = clock64();
 #endif
-#if !defined(HC_FIN_PREFETCH)
-#define HC_FIN_PREFETCH 0   // measured (profiles/r2_s8_micro.log): prefetching the finalize / store lines of a last-step lane gains nothing (56.7 vs 57.4 ms Strang, 88.8 vs 90.9 ms SDC at 256^3)
-#endif
-            if (HC_FIN_PREFETCH && act0) {
-                // a step attempt that reaches tout ends the integration if it passes: get the lines the finalize step / the store will wait for
-                // on their way now (SDC path: finalize and store happen at the end of THIS chain; Strang path: the store follows one round later)
-                const bool last_step = (ln.pc == PC_NLS_RES || ln.pc == PC_LSETUP_F) && ((ln.tn - c.tout) * ln.h >= 0.0);
-                if (last_step) prefetch_finalize_cell<PATH>(a, cell0, cell1);
-            }
             if (act0) {
                 // (SDC path) the cell data only the finalize step reads is fetched again when a lane gets there: it is not part of the lane state
                 if (PATH == PATH_STRUCT && ln.pc == PC_FINAL_EOS) load_finalize_cell(ln, a, cell0, cell1);
@@ -315,7 +270,7 @@ __global__ void __launch_bounds__(LANES, HC_SORTED_CTAS) hc_sorted_kernel(const 
         HC_TICK(19);
 
         // ================= phase S: stable counting sort of the lanes by integrator phase
-        if (HC_SORT_EVERY == 1 || (round % HC_SORT_EVERY) == 0) {
+        {
             const unsigned same = __match_any_sync(0xffffffffu, key);
             const int rank = __popc(same & lt_mask);
             if (lane_id < NKEY) s_cnt[lane_id * L::WARPS + warp] = 0;

@@ -219,29 +219,6 @@ __device__ __forceinline__ void load_finalize_cell(LaneT& ln, const KernelArgs& 
     ln.rhoe_new = t.f[F_SNEW].p[no + EINT * t.f[F_SNEW].nstride];
 }
 
-// The finalize step of a cell waits for DRAM twice if nothing is done about it: the finalize-only inputs (SDC path) and the read-modify-write
-// of (rho e, rho E) in store_cell.  A lane whose current step attempt reaches tout -- known before the bookkeeping chain starts -- therefore
-// prefetches those lines; by the time the chain gets to the finalize step they are in L1 / L2.
-__device__ __forceinline__ void prefetch_line(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-template <int PATH>
-__device__ __forceinline__ void prefetch_finalize_cell(const KernelArgs& a, unsigned cell0, unsigned cell1) {
-    int tile, i, j, k;
-    unpack_cell(a, cell0, cell1, tile, i, j, k);
-    const TileDesc& t = a.tiles[tile];
-    if (PATH == PATH_STRUCT && a.k.sdc_has_src) {
-        prefetch_line(t.f[F_HSRC].p + fab_off(t.f[F_HSRC], i, j, k) + EINT * t.f[F_HSRC].nstride);
-        prefetch_line(t.f[F_RSRC].p + fab_off(t.f[F_RSRC], i, j, k));
-        const double* pn = t.f[F_SNEW].p + fab_off(t.f[F_SNEW], i, j, k);
-        prefetch_line(pn + DENS * t.f[F_SNEW].nstride);
-        prefetch_line(pn + EINT * t.f[F_SNEW].nstride);
-        prefetch_line(pn + EDEN * t.f[F_SNEW].nstride);
-    } else {
-        const double* ps = t.f[F_STATE].p + fab_off(t.f[F_STATE], i, j, k);
-        prefetch_line(ps + EINT * t.f[F_STATE].nstride);
-        prefetch_line(ps + EDEN * t.f[F_STATE].nstride);
-    }
-}
-
 // scatter a finished cell (HOT LOOP C: integrate_state_vec_3d.cpp:317-321, f_rhs_struct.H:290-291,438-444)
 __device__ __forceinline__ long long cell_index(const TileDesc& t, int i, int j, int k) {
     return t.offset + ((long long)(k - t.lo[2]) * t.ny + (j - t.lo[1])) * t.nx + (i - t.lo[0]);
