@@ -21,11 +21,19 @@ def build(what="all"):
     subprocess.run(["make", "-s", "-C", HERE, what], check=True)
 
 
+def _p(x):
+    """pointer to the data of a numpy array, or of a torch tensor (device memory: the GPU flavour of the drop-in's test build takes device FABs)"""
+    if hasattr(x, "data_ptr"):
+        assert x.is_contiguous() and x.element_size() == 8
+        return C.cast(x.data_ptr(), _dp)
+    assert x.dtype == np.float64 and x.flags["C_CONTIGUOUS"]
+    return x.ctypes.data_as(_dp)
+
+
 def _ptrs(arrs):
     a = (_dp * len(arrs))()
     for i, x in enumerate(arrs):
-        assert x.dtype == np.float64 and x.flags["C_CONTIGUOUS"]
-        a[i] = x.ctypes.data_as(_dp)
+        a[i] = _p(x)
     return a
 
 
@@ -116,15 +124,15 @@ class Reference:
         """cell loop of Nyx::compute_new_temp over one box (restated around the reference's EOS functions, ref_driver.cpp)"""
         b, bp = self._boxes([box])
         self.lib.nyxref_compute_new_temp.argtypes = [C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int, _dp, _dp, C.c_double, C.c_double, C.c_double, C.c_int]
-        self.lib.nyxref_compute_new_temp(bp, ng_state, ng_diag, diag.shape[0], state.ctypes.data_as(_dp), diag.ctypes.data_as(_dp), a,
+        self.lib.nyxref_compute_new_temp(bp, ng_state, ng_diag, diag.shape[0], _p(state), _p(diag), a,
                                          small_temp, large_temp, max_temp_dt)
 
     def reset_internal_energy(self, box, state, diag, reset_src, a, small_temp, interp=0, ng_state=0, ng_diag=0, ng_reset=0):
         """cell loop of Nyx::reset_internal_energy over one box: the reference's reset_internal_e.H"""
         b, bp = self._boxes([box])
         self.lib.nyxref_reset_internal_energy.argtypes = [C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, C.c_double, C.c_double, C.c_int]
-        self.lib.nyxref_reset_internal_energy(bp, ng_state, ng_diag, diag.shape[0], ng_reset, state.ctypes.data_as(_dp), diag.ctypes.data_as(_dp),
-                                              reset_src.ctypes.data_as(_dp), a, small_temp, interp)
+        self.lib.nyxref_reset_internal_energy(bp, ng_state, ng_diag, diag.shape[0], ng_reset, _p(state), _p(diag),
+                                              _p(reset_src), a, small_temp, interp)
 
     def update_state_with_sources(self, boxes, s_old, s_new, ext_src, hydro_src, grav, reset_src, dt, a_old, a_new, small_dens, small_temp,
                                   ng=(0, 0, 0, 0, 0, 0)):
@@ -142,7 +150,7 @@ class Reference:
         self.lib.nyxref_enforce_min_cons_iter.restype = C.c_double
         self.lib.nyxref_enforce_min_cons_iter.argtypes = [C.POINTER(C.c_int), C.c_int, C.c_int, _dp, _dp, _dp, C.c_double, C.c_int]
         return self.lib.nyxref_enforce_min_cons_iter(box, ng_new, ng_rs, sborder.ctypes.data_as(_dp), s_new.ctypes.data_as(_dp),
-                                                     reset_src.ctypes.data_as(_dp), small_dens, sdc)
+                                                     _p(reset_src), small_dens, sdc)
 
     def ion_n(self, JH, JHe, U, nh, ne, gm1, hsp, z):
         out = np.zeros(4)

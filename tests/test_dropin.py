@@ -194,3 +194,57 @@ def test_dropin_update_state_with_sources_vs_reference(dropin, reference, low):
         for bi in range(len(d["boxes"])):
             assert np.array_equal(out[0][k][bi], out[1][k][bi]), (k, bi)
     assert any(not np.array_equal(a, b) for a, b in zip(out[0]["s_new"], d["s_new"]))
+
+
+@pytest.mark.gpu
+def test_dropin_gpu_flavour_takes_device_fabs(dropin, built):
+    """the AMREX_USE_GPU branch of the drop-in (what a GPU build of AMReX compiles: device-pointer entry points hc_*_batch on AMReX's stream,
+    no staging) against the CPU-AMReX branch (hc_*_host) on the same inputs: tests/_build/libnyx_dropin_shim_gpu.so is the same two
+    translation units compiled with -DAMREX_USE_GPU, the FAB pointers handed to it are device memory.  Every output is the same bits."""
+    import torch
+    from oracle import pyref
+    gpu = pyref.Reference(path=os.path.join(os.path.dirname(built.build_dropin_check()), "libnyx_dropin_shim_gpu.so"))
+    dev = lambda arrs: [torch.from_numpy(x).cuda() for x in arrs]            # noqa: E731
+    # Strang, grown boxes (two boxes with ghost cells)
+    z, n, ng_s = 3.0, 16, 4
+    a, dt = 1.0 / (1.0 + z), 0.5 * synth.step_dt(z)
+    boxes, S, D = _boxes_with_ghosts(n, ng_s, 4, z, (521, 522))
+    Sd, Dd = dev(S), dev(D)
+    assert dropin.integrate_state_vec(boxes, S, D, a, dt, ng_state=ng_s, ng_diag=4, grown=True) == 0
+    assert gpu.integrate_state_vec(boxes, Sd, Dd, a, dt, ng_state=ng_s, ng_diag=4, grown=True) == 0
+    torch.cuda.synchronize()
+    for h, d in zip(S + D, Sd + Dd):
+        assert h.tobytes() == d.cpu().numpy().tobytes()
+    # SDC
+    d0 = util.sdc_inputs(z, n, 523, 0.02)
+    order = ("s_old", "s_new", "diag", "hydro_src", "ir", "reset_src")
+    box = [(0, 0, 0, n - 1, n - 1, n - 1)]
+    h = {k: d0[k].copy() for k in order}
+    g = {k: torch.from_numpy(d0[k]).cuda() for k in order}
+    assert dropin.integrate_state_struct(box, *[[h[k]] for k in order], d0["a"], d0["a_end"], d0["dt"], 0) == 0
+    assert gpu.integrate_state_struct(box, *[[g[k]] for k in order], d0["a"], d0["a_end"], d0["dt"], 0) == 0
+    torch.cuda.synchronize()
+    for k in order:
+        assert h[k].tobytes() == g[k].cpu().numpy().tobytes(), k
+    # the rows either side: compute_new_temp, reset_internal_energy, update_state_with_sources (floor variant with cells below small_dens)
+    st, dg = synth.make_fab((n, n, n), seed=524, z=z)
+    std, dgd = torch.from_numpy(st).cuda(), torch.from_numpy(dg).cuda()
+    bx = (0, 0, 0, n - 1, n - 1, n - 1)
+    dropin.compute_new_temp(bx, st, dg, a, 1.0e-2, 1.0e9, 0)
+    gpu.compute_new_temp(bx, std, dgd, a, 1.0e-2, 1.0e9, 0)
+    rs, rsd = np.zeros((1, n, n, n)), torch.zeros((1, n, n, n), dtype=torch.float64, device="cuda")
+    dropin.reset_internal_energy(bx, st, dg, rs, a, 1.0e-2)
+    gpu.reset_internal_energy(bx, std, dgd, rsd, a, 1.0e-2)
+    torch.cuda.synchronize()
+    assert st.tobytes() == std.cpu().numpy().tobytes() and dg.tobytes() == dgd.cpu().numpy().tobytes() and rs.tobytes() == rsd.cpu().numpy().tobytes()
+    src = util.sources_inputs(seed=525, low_density_cells=5)
+    slots = ("s_old", "s_new", "ext_src", "hydro_src", "grav", "reset_src")
+    hs = {k: [x.copy() for x in src[k]] for k in slots}
+    gs = {k: dev(src[k]) for k in slots}
+    for lib, arrs in ((dropin, hs), (gpu, gs)):
+        lib.update_state_with_sources(src["boxes"], *[arrs[k] for k in slots], src["dt"], src["a_old"], src["a_new"], src["small_dens"], src["small_temp"],
+                                      ng=src["ng"])
+    torch.cuda.synchronize()
+    for k in slots:
+        for x, y in zip(hs[k], gs[k]):
+            assert x.tobytes() == y.cpu().numpy().tobytes(), k
