@@ -20,6 +20,8 @@ CXXFLAGS="${CMD%% -Xlinker*}"
 # Nyx::update_state_with_sources (floor and conservative enforce_minimum_density) in place of the reference's translation unit
 ( cd "$WORK/LyA" && $CXXFLAGS -I"$ROOT/include" -c "$ROOT/nyx_b200/csrc/nyx_sources_dropin.cpp" -o "$WORK/nyx_sources_dropin.o" )
 [ -f "$WORK/hctest_replay_ref.o" ] || ( cd "$WORK/LyA" && $CXXFLAGS -c "$HERE/golden/hctest_replay_ref.cpp" -o "$WORK/hctest_replay_ref.o" )
+# the non-SDC signature of Nyx::update_state_with_sources (no reset_e_src argument): syntax check against the real headers without -DSDC
+( cd "$WORK/LyA" && ${CXXFLAGS// -DSDC/} -I"$ROOT/include" -fsyntax-only "$ROOT/nyx_b200/csrc/nyx_sources_dropin.cpp" )
 KEEP=$(ls "$OBJ"/*.o | grep -v -e '/integrate_state_vec_3d.o' -e '/integrate_state_with_source_3d.o')
 LIBS="-L$WORK/sundials_inst/lib -lsundials_cvode -lsundials_nvecserial -lsundials_nvecopenmp -L$ROOT/nyx_b200/csrc -lnyx_hc -Wl,-rpath,/root/repo/nyx_b200/csrc -Wl,-rpath,$ROOT/nyx_b200/csrc"
 /usr/bin/g++ -fopenmp -pthread -o "$OUT/Nyx3d.dropin.ex" $KEEP "$WORK/nyx_heatcool_dropin.o" $LIBS
