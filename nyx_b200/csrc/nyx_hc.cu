@@ -16,6 +16,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <climits>
 #include <atomic>
 #include <cstdarg>
 #include <cstdint>
@@ -829,6 +830,8 @@ int launch(int path, int ntiles, const HcFab* const* fabs, int nf, const HcBox* 
 struct HostSlot {
     const HcFab* host;          // ntiles host FABs
     std::vector<int> in, out;   // components copied to the device before / back to the host after the kernel
+    int halo = 0;               // cells around a tile its kernel reads from this FAB (the border copy of the conservative density fix: 2)
+    bool whole = false;         // the kernel indexes this FAB outside the tile's index range (the coarse zhi FAB of init_zhi): always copied whole
 };
 struct HostPipe {
     cudaStream_t h2d = nullptr, comp = nullptr, comp2 = nullptr, d2h = nullptr;
@@ -877,25 +880,33 @@ int host_pipe(int dev, HostPipe*& hp) {
 
 using GroupLauncher = std::function<int(int n, const HcFab* const* fabs, const HcBox* tiles, cudaStream_t stream)>;
 
-// D2H of component c of one FAB restricted to the cells of `b` (the tile): used for components that were NOT uploaded (pure outputs), so
-// that host cells outside the tile -- ghost cells, other tiles of the same FAB -- keep their values.  Contiguous when the tile spans the
-// FAB in x and y (one block of nz planes), a pitched 3-D copy otherwise.
+// Copy of component c of one FAB restricted to the cells of `b`, device <-> host (same strides on both sides).  D2H of the tile: components
+// that were NOT uploaded (pure outputs), so that host cells outside the tile -- ghost cells, other tiles of the same FAB -- keep their values.
+// Both directions: FABs with ghost cells, of which only the tiles' cells (+ halo) are staged.  Contiguous when the box spans the FAB in x
+// and y (one block of nz planes), a pitched 3-D copy otherwise.
+int copy_box(const HcFab& h, const double* dbase, int c, const HcBox& b, cudaMemcpyKind kind, cudaStream_t stream);
 int copy_tile_d2h(const HcFab& h, const double* dbase, int c, const HcBox& b, cudaStream_t stream) {
+    return copy_box(h, dbase, c, b, cudaMemcpyDeviceToHost, stream);
+}
+int copy_box(const HcFab& h, const double* dbase, int c, const HcBox& b, cudaMemcpyKind kind, cudaStream_t stream) {
+    const bool d2h = (kind == cudaMemcpyDeviceToHost);
     const long long nx = b.hi[0] - b.lo[0] + 1, ny = b.hi[1] - b.lo[1] + 1, nz = b.hi[2] - b.lo[2] + 1;
     if (nx <= 0 || ny <= 0 || nz <= 0) return HC_OK;
     const long long off = (b.lo[0] - h.lo[0]) + (b.lo[1] - h.lo[1]) * h.jstride + (b.lo[2] - h.lo[2]) * h.kstride + (long long)c * h.nstride;
+    double* dev = const_cast<double*>(dbase) + off;
+    double* hst = h.p + off;
     if (nx == h.jstride && ny * h.jstride == h.kstride) {
-        CUDA_TRY(cudaMemcpyAsync(h.p + off, dbase + off, (size_t)(nz * h.kstride) * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaMemcpyAsync(d2h ? hst : dev, d2h ? dev : hst, (size_t)(nz * h.kstride) * sizeof(double), kind, stream));
         return HC_OK;
     }
     if (h.kstride % h.jstride != 0) { set_err("FAB strides are not those of a box (kstride is not a multiple of jstride)"); return HC_ERR_ARG; }
     cudaMemcpy3DParms prm{};
     const size_t pitch = (size_t)h.jstride * sizeof(double), rows = (size_t)(h.kstride / h.jstride);
     // the pitched pointers start at the tile's first cell: the row pitch and the rows per plane are the FAB's
-    prm.srcPtr = make_cudaPitchedPtr(const_cast<double*>(dbase) + off, pitch, (size_t)nx * sizeof(double), rows);
-    prm.dstPtr = make_cudaPitchedPtr(h.p + off, pitch, (size_t)nx * sizeof(double), rows);
+    prm.srcPtr = make_cudaPitchedPtr(d2h ? dev : hst, pitch, (size_t)nx * sizeof(double), rows);
+    prm.dstPtr = make_cudaPitchedPtr(d2h ? hst : dev, pitch, (size_t)nx * sizeof(double), rows);
     prm.extent = make_cudaExtent((size_t)nx * sizeof(double), (size_t)ny, (size_t)nz);
-    prm.kind = cudaMemcpyDeviceToHost;
+    prm.kind = kind;
     CUDA_TRY(cudaMemcpy3DAsync(&prm, stream));
     return HC_OK;
 }
@@ -1007,6 +1018,32 @@ int run_host(int path, int ntiles, std::vector<HostSlot>& slots, const HcBox* ti
             hp->slab_busy[b] = false;
         }
         if (hp->slab_busy[b]) CUDA_TRY(cudaStreamWaitEvent(hp->h2d, hp->slab_free[b], 0));
+        // What travels of a FAB: the bounding box of its tiles in this group (+ the slot's halo), clipped to the FAB -- or the whole
+        // components (one contiguous copy each) when that box is most of the FAB anyway.  A state FAB of Nyx carries 4 ghost cells: a 32^3
+        // box is 51 % of its 40^3 FAB, a 128^3 box 83 % of 136^3.
+        std::vector<std::vector<HcBox>> stage(nf, std::vector<HcBox>(n));
+        std::vector<std::vector<char>> whole(nf, std::vector<char>(n, 1));
+        for (int s = 0; s < nf; ++s)
+            for (int i = 0; i < n; ++i) {
+                if (first_of(s, i) != i) continue;
+                const HcFab& h = slots[s].host[t0 + i];
+                HcBox bb{{INT_MAX, INT_MAX, INT_MAX}, {INT_MIN, INT_MIN, INT_MIN}};
+                for (int j = i; j < n && first_of(s, j) == i; ++j)
+                    for (int d = 0; d < 3; ++d) {
+                        if (tiles[t0 + j].hi[d] < tiles[t0 + j].lo[d]) continue;
+                        bb.lo[d] = std::min(bb.lo[d], tiles[t0 + j].lo[d] - slots[s].halo);
+                        bb.hi[d] = std::max(bb.hi[d], tiles[t0 + j].hi[d] + slots[s].halo);
+                    }
+                long long vol = 1, fvol = 1;
+                for (int d = 0; d < 3; ++d) {
+                    bb.lo[d] = std::max(bb.lo[d], h.lo[d]); bb.hi[d] = std::min(bb.hi[d], h.hi[d]);
+                    vol *= std::max(0, bb.hi[d] - bb.lo[d] + 1); fvol *= std::max(1, h.hi[d] - h.lo[d] + 1);
+                }
+                stage[s][i] = bb;
+                // (strides that are not those of the FAB's own box: whole components, the pitched copy assumes them)
+                const bool box_strides = h.jstride == (long long)(h.hi[0] - h.lo[0] + 1) && h.kstride == h.jstride * (h.hi[1] - h.lo[1] + 1);
+                whole[s][i] = (slots[s].whole || !box_strides || vol * 100 >= fvol * 85) ? 1 : 0;
+            }
         size_t off = 0;
         for (int s = 0; s < nf; ++s) {
             dfab[s].assign(slots[s].host + t0, slots[s].host + t1);
@@ -1019,8 +1056,9 @@ int run_host(int path, int ntiles, std::vector<HostSlot>& slots, const HcBox* ti
                 dfab[s][i].p = d;
                 for (int c : slots[s].in) {
                     if (c >= h.ncomp) continue;
-                    CUDA_TRY(cudaMemcpyAsync(d + (size_t)c * h.nstride, h.p + (size_t)c * h.nstride, (size_t)h.nstride * sizeof(double),
-                                             cudaMemcpyHostToDevice, hp->h2d));
+                    if (whole[s][i]) CUDA_TRY(cudaMemcpyAsync(d + (size_t)c * h.nstride, h.p + (size_t)c * h.nstride, (size_t)h.nstride * sizeof(double),
+                                                              cudaMemcpyHostToDevice, hp->h2d));
+                    else if (int rc2 = copy_box(h, d, c, stage[s][i], cudaMemcpyHostToDevice, hp->h2d)) return rc2;
                 }
             }
         }
@@ -1048,11 +1086,11 @@ int run_host(int path, int ntiles, std::vector<HostSlot>& slots, const HcBox* ti
                 for (int c : slots[s].out) {
                     if (c >= h.ncomp) continue;
                     const bool uploaded = std::find(slots[s].in.begin(), slots[s].in.end(), c) != slots[s].in.end();
-                    if (uploaded) {
+                    if (uploaded && whole[s][first_of(s, i)]) {
                         // the device copy holds the whole component: one contiguous copy per FAB
                         if (owner) CUDA_TRY(cudaMemcpyAsync(h.p + (size_t)c * h.nstride, dfab[s][i].p + (size_t)c * h.nstride, (size_t)h.nstride * sizeof(double),
                                                             cudaMemcpyDeviceToHost, hp->d2h));
-                    } else if (int rc2 = copy_tile_d2h(h, dfab[s][i].p, c, tiles[t0 + i], hp->d2h)) return rc2;   // pure output: the tile's cells only
+                    } else if (int rc2 = copy_tile_d2h(h, dfab[s][i].p, c, tiles[t0 + i], hp->d2h)) return rc2;   // the tile's cells only (pure outputs; FABs staged by sub-box)
                 }
             }
         CUDA_TRY(cudaEventRecord(hp->slab_free[b], hp->d2h));
@@ -1518,7 +1556,7 @@ int hc_enforce_min_density_cons_iter_host(int ntiles, const HcFab* sborder, cons
     if (int rc = new_cons_words(dmm, hp->comp)) return rc;
     const std::vector<int> all6 = {0, 1, 2, 3, 4, 5};
     const HcSrcParams p = *prm;
-    std::vector<HostSlot> slots = {{sborder, all6, {}}, {s_new, all6, all6}};
+    std::vector<HostSlot> slots = {{sborder, all6, {}, 2}, {s_new, all6, all6}};   // the kernel reads the border copy two cells around a tile
     if (p.sdc) slots.push_back({reset_src, {}, {0}});
     GroupLauncher iter = [&](int n, const HcFab* const* fabs, const HcBox* tl, cudaStream_t st) { return launch_cons_iter(n, fabs, tl, p, dmm, st); };
     const int rc = run_host(-1, ntiles, slots, tiles, Consts{}, nullptr, nullptr, &iter);
@@ -1645,7 +1683,7 @@ int hc_init_zhi_host(int ntiles, const HcFab* diag, const HcFab* zhi, int ratio,
     if (ntiles < 0 || (ntiles > 0 && (!diag || !zhi || !tiles)) || ratio < 1) { set_err("bad argument"); return HC_ERR_ARG; }
     if (ntiles == 0) return HC_OK;
     // diag(Zhi) is a pure output (only the tile's cells travel back), the coarse zhi FAB a pure input
-    std::vector<HostSlot> slots = {{diag, {}, {ZHI}}, {zhi, {0}, {}}};
+    std::vector<HostSlot> slots = {{diag, {}, {ZHI}}, {zhi, {0}, {}, 0, true}};   // zhi lives on the coarse index space: whole
     GroupLauncher fill = [&](int n, const HcFab* const* fabs, const HcBox* tl, cudaStream_t st) {
         return hc_init_zhi_batch(n, fabs[0], fabs[1], ratio, tl, st);
     };

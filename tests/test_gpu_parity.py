@@ -314,6 +314,57 @@ def test_host_buffer_api(hc_lib, port):
     assert np.median(np.abs(d["ir"][0] - ref["ir"][0])) / np.abs(ref["ir"][0]).max() < 1e-9
 
 
+def test_host_buffer_api_stages_only_the_tiles_of_ghosted_fabs(hc_lib):
+    """host-buffer entry points on FABs with wide ghost regions (12^3 tiles inside 24^3 FABs: the tiles are 12.5 % of the FAB): only the
+    bounding box of the tiles travels, so NaN-poisoned ghost cells of the inputs never reach the device and every ghost cell of every
+    host FAB keeps its bytes; the valid cells equal those of the device-resident call, bit for bit.  Two tiles that share one FAB (sub-box =
+    their union) and a tile in a FAB of its own, Strang and SDC."""
+    torch = _torch()
+    z, n, g = 3.0, 12, 6
+    m = n + 2 * g
+    a, dt = 1.0 / (1.0 + z), 0.5 * synth.step_dt(z)
+    inner = (slice(None),) + (slice(g, g + n),) * 3
+
+    def poisoned(arr):
+        out = np.full_like(arr, np.nan)
+        out[inner] = arr[inner]
+        return out
+    # ---- Strang: FAB A holds two tiles (split in x), FAB B one
+    sa, da = synth.make_fab((m, m, m), seed=61, z=z)
+    sb, db = synth.make_fab((m, m, m), seed=62, z=z)
+    host = [poisoned(x) for x in (sa, da, sb, db)]
+    before = [x.copy() for x in host]
+    lo = (-g, -g, -g)
+    tiles = [capi.make_box((0, 0, 0), (5, n - 1, n - 1)), capi.make_box((6, 0, 0), (n - 1, n - 1, n - 1)), capi.make_box((0, 0, 0), (n - 1, n - 1, n - 1))]
+    fs = [capi.fab_of_numpy(host[0], lo), capi.fab_of_numpy(host[0], lo), capi.fab_of_numpy(host[2], lo)]
+    fd = [capi.fab_of_numpy(host[1], lo), capi.fab_of_numpy(host[1], lo), capi.fab_of_numpy(host[3], lo)]
+    st = hc_lib.integrate_vec_host(fs, fd, tiles, a, dt)
+    assert st.n_cells == 2 * n ** 3 and st.n_failed == 0
+    dev = [torch.from_numpy(x).cuda() for x in (sa, da, sb, db)]
+    ds = [capi.fab_of_torch(dev[0], lo), capi.fab_of_torch(dev[0], lo), capi.fab_of_torch(dev[2], lo)]
+    dd = [capi.fab_of_torch(dev[1], lo), capi.fab_of_torch(dev[1], lo), capi.fab_of_torch(dev[3], lo)]
+    hc_lib.integrate_vec_batch(ds, dd, tiles, a, dt)
+    torch.cuda.synchronize()
+    ghost = np.ones((m, m, m), dtype=bool); ghost[g:g + n, g:g + n, g:g + n] = False
+    for h, b0, d in zip(host, before, dev):
+        assert h[inner].tobytes() == d.cpu().numpy()[inner].tobytes()
+        assert h[:, ghost].tobytes() == b0[:, ghost].tobytes()              # NaNs and all: untouched
+    assert not np.isnan(host[0][inner]).any() and (host[0][5][g:g + n, g:g + n, g:g + n] != before[0][5][g:g + n, g:g + n, g:g + n]).all()
+    # ---- SDC, one tile per FAB
+    d0 = util.sdc_inputs(z, m, 63, 0.05)
+    names = ("s_old", "diag", "s_new", "hydro_src", "reset_src", "ir")
+    hh = {k: poisoned(d0[k]) for k in names}
+    b1 = {k: v.copy() for k, v in hh.items()}
+    gg = {k: torch.from_numpy(d0[k]).cuda() for k in names}
+    t1 = [capi.make_box((0, 0, 0), (n - 1, n - 1, n - 1))]
+    hc_lib.integrate_struct_host(*[[capi.fab_of_numpy(hh[k], lo)] for k in names], t1, d0["a"], d0["a_end"], d0["dt"], 0)
+    hc_lib.integrate_struct_batch(*[[capi.fab_of_torch(gg[k], lo)] for k in names], t1, d0["a"], d0["a_end"], d0["dt"], 0)
+    torch.cuda.synchronize()
+    for k in names:
+        assert hh[k][inner].tobytes() == gg[k].cpu().numpy()[inner].tobytes(), k
+        assert hh[k][:, ghost].tobytes() == b1[k][:, ghost].tobytes(), k
+
+
 def test_eos_kernel(hc_lib, port):
     torch = _torch()
     z, n = 3.0, 16
